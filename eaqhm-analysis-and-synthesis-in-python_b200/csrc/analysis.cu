@@ -1,0 +1,749 @@
+// Stage A of one eaQHM adaptation: per-frame basis construction, weighted complex Gram,
+// Cholesky solve, frequency mismatch and acceptance (reference: functions.py:176-329,
+// iqhmLS_complexamps :420-470, eaqhmLS_complexamps :472-535).  sm_100a, FP64.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBasisThreads = 256;
+constexpr int kBasisWarps = kBasisThreads / 32;
+constexpr int kNb = 16;   // Cholesky block width
+
+struct AnaArgs {
+    eaqhm_tables t;
+    const double* s;
+    const double* am_cur;
+    const double* fm_cur;
+    eaqhm_knots k;
+    double* best_am;
+    int32_t adapt;
+    int32_t j0, nf;                 // chunk of the analysed list: [j0, j0+nf)
+    int32_t nnz_max, Mmax, Pmax, Pp, Lp;
+    uint8_t* fb;                    // [G] fallback flags of this adaptation
+    int32_t* Mcols;                 // [chunk] columns of E2 per frame (2*nnz+1)
+    int32_t* Lrows;                 // [chunk] window samples per frame
+    int16_t* act;                   // [chunk][nnz_max] active harmonic indices
+    double2* Ew;                    // [chunk][Pmax][Lp]
+    double2* R;                     // [chunk][Pmax+1][Pp]   (row P = conj(rhs))
+    double2* x;                     // [chunk][Pmax]
+    int32_t* status;
+};
+
+// ---------------------------------------------------------------------------------------
+// fallback flags over ALL analysed frames (functions.py:204-210, quirk Q6): a frame whose
+// centre row of fm_current is entirely zero analyses a single 140 Hz / 10e-4 component.
+// The in-place amplitude write also lands in the previous adaptation's am_recon, which is
+// the am_fin snapshot (functions.py:383,400) -> best_am.
+// ---------------------------------------------------------------------------------------
+__global__ void k_fallback_flags(AnaArgs A) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= A.t.nA) return;
+    const int g = A.t.alist[w];
+    const int64_t c = A.t.pos[g];
+    bool any = false;
+    for (int k = lane; k < A.t.Kmax; k += 32) any |= (A.fm_cur[(int64_t)k * A.t.T + c] != 0.0);
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) {
+        A.fb[g] = any ? 0 : 1;
+        if (!any) {
+            atomicAdd(&A.status[1], 1);
+            if (A.best_am) A.best_am[g] = kFallbackAm;   // harmonic 0 row: [0][g]
+        }
+    }
+}
+
+// active set of each frame of the chunk (functions.py:202, 246-248); adaptation 0: all K0 harmonics
+__global__ void k_active(AnaArgs A) {
+    const int jl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (jl >= A.nf) return;
+    const int g = A.t.alist[A.j0 + jl];
+    int16_t* act = A.act + (int64_t)jl * A.nnz_max;
+    int count = 0;
+    if (A.adapt == 0) {
+        count = A.t.K0[g];
+        for (int k = lane; k < count; k += 32) act[k] = (int16_t)k;
+    } else if (A.fb[g]) {
+        count = 1;
+        if (lane == 0) act[0] = 0;
+    } else {
+        const int64_t c = A.t.pos[g];
+        for (int k0 = 0; k0 < A.t.Kmax; k0 += 32) {
+            const int k = k0 + lane;
+            const bool nzf = k < A.t.Kmax && A.fm_cur[(int64_t)k * A.t.T + c] != 0.0;
+            const unsigned b = __ballot_sync(0xffffffffu, nzf);
+            if (nzf) {
+                const int slot = count + __popc(b & ((1u << lane) - 1u));
+                if (slot < A.nnz_max) act[slot] = (int16_t)k;
+            }
+            count += __popc(b);
+        }
+        if (count > A.nnz_max) count = A.nnz_max;   // cannot happen: active set only shrinks
+    }
+    if (lane == 0) {
+        A.Mcols[jl] = 2 * count + 1;
+        A.Lrows[jl] = 2 * A.t.N[g] + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// basis: one CTA per frame, one warp per harmonic column pair (+f, time-reversed -f), plus DC.
+// Column order of E2: [0,nnz) positive harmonics, [nnz,2nnz) their mirrored partners, 2nnz = DC.
+// Unknown order of the LS system: p in [0,M) amplitudes, [M,2M) slopes (functions.py:455,519).
+// ---------------------------------------------------------------------------------------
+template <bool ADAPT>
+__global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jl = blockIdx.x;
+    const int g = A.t.alist[A.j0 + jl];
+    const int N = A.t.N[g], L = 2 * N + 1;
+    const int M = A.Mcols[jl], nz = (M - 1) / 2, P = 2 * M;
+    const int u = A.t.utt[g];
+    const int64_t us = A.t.ustart[u], ul = A.t.ulen[u];
+    const int64_t cl = A.t.pos[g] - us;
+    const double fs = A.t.fs;
+
+    double* w = reinterpret_cast<double*>(smem_raw);
+    double* ws = w + A.Lp;
+    double* fmw = ws + A.Lp + (size_t)warp * 2 * A.Lp;
+    double* amw = fmw + A.Lp;
+    int16_t* prv = reinterpret_cast<int16_t*>(ws + A.Lp + (size_t)kBasisWarps * 2 * A.Lp) + (size_t)warp * 2 * A.Lp;
+    int16_t* nxt = prv + A.Lp;
+
+    // analysis window (numpy.blackman / numpy.hamming, functions.py:194,200) and windowed signal
+    for (int n = tid; n < L; n += kBasisThreads) {
+        const double nn = (double)(1 - L + 2 * n), den = (double)(L - 1);
+        const double x1 = (kPi * nn) / den;
+        double wn;
+        if (ADAPT) wn = 0.54 + 0.46 * cos(x1);
+        else wn = 0.42 + 0.5 * cos(x1) + 0.08 * cos(((2.0 * kPi) * nn) / den);
+        int64_t il = cl - N + n;
+        if (il < 0) il += ul;                 // the reference's negative fancy index wraps
+        w[n] = wn;
+        ws[n] = wn * A.s[us + il];
+    }
+    __syncthreads();
+
+    double2* EwF = A.Ew + (size_t)jl * A.Pmax * A.Lp;
+    double2* Rb = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp + (size_t)P * A.Pp;   // row P: conj(rhs)
+    const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
+    const double f0 = A.t.f0[g];
+
+    for (int it = warp; it <= nz; it += kBasisWarps) {
+        if (it == nz) {   // DC column: E2 = 1 (fm = 0, am = 0 -> (eps+0)/(0+eps) = 1)
+            double s0 = 0.0, s1 = 0.0;
+            double2* e0 = EwF + (size_t)(2 * nz) * A.Lp;
+            double2* e1 = EwF + (size_t)(M + 2 * nz) * A.Lp;
+            for (int n = lane; n < L; n += 32) {
+                const double wn = w[n], nc = (double)(n - N);
+                e0[n] = make_double2(wn, 0.0);
+                e1[n] = make_double2(nc * wn, 0.0);
+                s0 += wn * ws[n];
+                s1 += nc * wn * ws[n];
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (lane == 0) { Rb[2 * nz] = make_double2(s0, 0.0); Rb[M + 2 * nz] = make_double2(s1, 0.0); }
+            continue;
+        }
+        const int k = act[it];
+        double2* ep0 = EwF + (size_t)it * A.Lp;
+        double2* ep1 = EwF + (size_t)(M + it) * A.Lp;
+        double2* en0 = EwF + (size_t)(nz + it) * A.Lp;
+        double2* en1 = EwF + (size_t)(M + nz + it) * A.Lp;
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+        if (!ADAPT) {
+            // functions.py:453-455: t = (n*2*pi*f)/fs with f = (k+1)*f0; the -f column is the conjugate
+            const double fk = (double)(k + 1) * f0;
+            for (int n = lane; n < L; n += 32) {
+                const double nc = (double)(n - N);
+                const double t = (((nc * 2.0) * kPi) * fk) / fs;
+                double sn, cs;
+                sincos(t, &sn, &cs);
+                const double wn = w[n], xr = cs * wn, xi = sn * wn, v = ws[n];
+                ep0[n] = make_double2(xr, xi);       ep1[n] = make_double2(nc * xr, nc * xi);
+                en0[n] = make_double2(xr, -xi);      en1[n] = make_double2(nc * xr, -(nc * xi));
+                acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+            }
+            acc[4] = acc[0]; acc[5] = -acc[1]; acc[6] = acc[2]; acc[7] = -acc[3];
+        } else {
+            // 1. gather the window of fm_current / am_current (functions.py:244-245); column 0 sees the
+            //    in-place fallback writes of this and earlier frames (Q6, functions.py:209-210)
+            const double* fmk = A.fm_cur + (int64_t)k * A.t.T + us;
+            const double* amk = A.am_cur + (int64_t)k * A.t.T + us;
+            for (int n = lane; n < L; n += 32) {
+                int64_t il = cl - N + n;
+                if (il < 0) il += ul;
+                double f = fmk[il], a = amk[il];
+                if (k == 0 && (il % A.t.step) == 0) {
+                    const int64_t gi = A.t.gfirst[u] + il / A.t.step;
+                    if (gi <= g && gi < A.t.gfirst[u] + A.t.gcount[u] && A.fb[gi]) { f = kFallbackFm; a = kFallbackAm; }
+                }
+                fmw[n] = f; amw[n] = a;
+            }
+            __syncwarp();
+            // 2. nearest non-zero neighbour on each side (functions.py:253-271)
+            int carry = -1;
+            for (int base = 0; base < L; base += 32) {
+                const int n = base + lane;
+                const bool nzf = n < L && fmw[n] != 0.0;
+                const unsigned b = __ballot_sync(0xffffffffu, nzf);
+                const unsigned m = b & (0xffffffffu >> (31 - lane));
+                if (n < L) prv[n] = (int16_t)(m ? base + 31 - __clz(m) : carry);
+                if (b) carry = base + 31 - __clz(b);
+            }
+            carry = -1;
+            for (int base = ((L - 1) / 32) * 32; base >= 0; base -= 32) {
+                const int n = base + lane;
+                const bool nzf = n < L && fmw[n] != 0.0;
+                const unsigned b = __ballot_sync(0xffffffffu, nzf);
+                const unsigned m = b & (0xffffffffu << lane);
+                if (n < L) nxt[n] = (int16_t)(m ? base + __ffs(m) - 1 : carry);
+                if (b) carry = base + __ffs(b) - 1;
+            }
+            __syncwarp();
+            // 3. edge hold + linear gap fill through numpy.interp's formula (functions.py:277-278)
+            for (int n = lane; n < L; n += 32) {
+                if (fmw[n] == 0.0) {
+                    const int p = prv[n], q = nxt[n];
+                    double f, a;
+                    if (p < 0 && q < 0) { f = 0.0; a = amw[n]; }
+                    else if (p < 0) { f = fmw[q]; a = amw[q]; }
+                    else if (q < 0) { f = fmw[p]; a = amw[p]; }
+                    else {
+                        const double dx = (double)(q - p), xx = (double)(n - p);
+                        f = ((fmw[q] - fmw[p]) / dx) * xx + fmw[p];
+                        a = ((amw[q] - amw[p]) / dx) * xx + amw[p];
+                    }
+                    // neighbours are non-zero samples: never written here, and zero samples are read by no other lane
+                    fmw[n] = f; amw[n] = a;
+                }
+            }
+            __syncwarp();
+            // 4. running sum of the frequency track (functions.py:509-511; lfilter == cumsum)
+            double run = 0.0;
+            for (int base = 0; base < L; base += 32) {
+                const int n = base + lane;
+                double v = n < L ? fmw[n] : 0.0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += t;
+                }
+                v += run;
+                if (n < L) fmw[n] = v;
+                run = __shfl_sync(0xffffffffu, v, 31);
+            }
+            __syncwarp();
+            // 5. +f column (functions.py:513-519) and the time-reversed -f column (Q2, :284-285):
+            //    cumsum of -fm[::-1] minus its centre value equals S[L-2-n] - S[N-1]
+            const double Smid = fmw[N], Smid1 = fmw[N - 1], aden = amw[N] + kAmEps;
+            for (int n = lane; n < L; n += 32) {
+                const double nc = (double)(n - N), wn = w[n], v = ws[n];
+                double sn, cs;
+                {
+                    const double t = (kTwoPi * (fmw[n] - Smid)) / fs;
+                    sincos(t, &sn, &cs);
+                    const double r = (kAmEps + amw[n]) / aden;
+                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                    ep0[n] = make_double2(xr, xi);   ep1[n] = make_double2(nc * xr, nc * xi);
+                    acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+                }
+                {
+                    const int m2 = L - 2 - n;
+                    const double Sm = m2 >= 0 ? fmw[m2] : 0.0;
+                    const double t = (kTwoPi * (Sm - Smid1)) / fs;
+                    sincos(t, &sn, &cs);
+                    const double r = (kAmEps + amw[L - 1 - n]) / aden;
+                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                    en0[n] = make_double2(xr, xi);   en1[n] = make_double2(nc * xr, nc * xi);
+                    acc[4] += xr * v; acc[5] += xi * v; acc[6] += nc * xr * v; acc[7] += nc * xi * v;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) {
+            Rb[it] = make_double2(acc[0], acc[1]);           Rb[M + it] = make_double2(acc[2], acc[3]);
+            Rb[nz + it] = make_double2(acc[4], acc[5]);      Rb[M + nz + it] = make_double2(acc[6], acc[7]);
+        }
+        __syncwarp();
+    }
+}
+
+// explicit-column basis for the eaqhmLS_complexamps seam (functions.py:472-519): am, fm [L][M] row-major
+__global__ void k_basis_explicit(const double* s, const double* am, const double* fm, const double* win,
+                                 int L, int M, double fs, double2* Ew, int Lp, double2* Rb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* S = reinterpret_cast<double*>(smem_raw) + (size_t)(threadIdx.x >> 5) * Lp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int mid = (L - 1) / 2;
+    for (int c = warp; c < M; c += nw) {
+        double run = 0.0;
+        for (int base = 0; base < L; base += 32) {
+            const int n = base + lane;
+            double v = n < L ? fm[(size_t)n * M + c] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            v += run;
+            if (n < L) S[n] = v;
+            run = __shfl_sync(0xffffffffu, v, 31);
+        }
+        __syncwarp();
+        const double Smid = S[mid], aden = am[(size_t)mid * M + c] + kAmEps;
+        double acc[4] = {0, 0, 0, 0};
+        for (int n = lane; n < L; n += 32) {
+            const double nc = (double)(n - mid), wn = win[n], v = wn * s[n];
+            double sn, cs;
+            sincos((kTwoPi * (S[n] - Smid)) / fs, &sn, &cs);
+            const double r = (kAmEps + am[(size_t)n * M + c]) / aden;
+            const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+            Ew[(size_t)c * Lp + n] = make_double2(xr, xi);
+            Ew[(size_t)(M + c) * Lp + n] = make_double2(nc * xr, nc * xi);
+            acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) { Rb[c] = make_double2(acc[0], acc[1]); Rb[M + c] = make_double2(acc[2], acc[3]); }
+        __syncwarp();
+    }
+}
+
+// explicit-frequency basis for the iqhmLS_complexamps seam (functions.py:420-464)
+__global__ void k_basis_harmonic_explicit(const double* s, const double* f0range, const double* win, int L, int M,
+                                          double fs, double2* Ew, int Lp, double2* Rb) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double midlen = (double)(L - 1) / 2.0;
+    for (int c = warp; c < M; c += nw) {
+        const double fk = f0range[c];
+        double acc[4] = {0, 0, 0, 0};
+        for (int n = lane; n < L; n += 32) {
+            const double nc = (double)n - midlen, wn = win[n], v = wn * s[n];
+            double sn, cs;
+            sincos((((nc * 2.0) * kPi) * fk) / fs, &sn, &cs);
+            const double xr = cs * wn, xi = sn * wn;
+            Ew[(size_t)c * Lp + n] = make_double2(xr, xi);
+            Ew[(size_t)(M + c) * Lp + n] = make_double2(nc * xr, nc * xi);
+            acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) { Rb[c] = make_double2(acc[0], acc[1]); Rb[M + c] = make_double2(acc[2], acc[3]); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gram R = Ew^H Ew, lower triangle (functions.py:459,524).  v1: 32x32 complex tiles, DFMA.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram(SolveArgs A) {
+    const int jl = blockIdx.y;
+    const int P = 2 * A.Mcols[jl], L = A.Lrows[jl];
+    const int tp = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * tp + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > tp) ti--;
+    while ((ti + 1) * (ti + 2) / 2 <= tp) ti++;
+    const int tj = tp - ti * (ti + 1) / 2;
+    if (ti * 32 >= P) return;
+    __shared__ double2 As[32][33], Bs[32][33];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const double2* EwF = A.Ew + (size_t)jl * A.Pmax * A.Lp;
+    double2 acc[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) acc[i][j] = make_double2(0.0, 0.0);
+    for (int n0 = 0; n0 < L; n0 += 32) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int idx = tid + e * 256, r = idx >> 5, nn = idx & 31;
+            const int n = n0 + nn, pa = ti * 32 + r, pb = tj * 32 + r;
+            As[r][nn] = (pa < P && n < L) ? EwF[(size_t)pa * A.Lp + n] : make_double2(0.0, 0.0);
+            Bs[r][nn] = (pb < P && n < L) ? EwF[(size_t)pb * A.Lp + n] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int nn = 0; nn < 32; nn++) {
+            const double2 a0 = As[ty * 2][nn], a1 = As[ty * 2 + 1][nn];
+            const double2 b0 = Bs[tx * 2][nn], b1 = Bs[tx * 2 + 1][nn];
+            cfma_conj_a(acc[0][0], a0, b0); cfma_conj_a(acc[0][1], a0, b1);
+            cfma_conj_a(acc[1][0], a1, b0); cfma_conj_a(acc[1][1], a1, b1);
+        }
+        __syncthreads();
+    }
+    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int p = ti * 32 + ty * 2 + i, q = tj * 32 + tx * 2 + j;
+            if (p < P && q <= p) RF[(size_t)p * A.Pp + q] = acc[i][j];
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// Cholesky of the augmented matrix [[R, b],[b^H, .]] (left-looking, block width 16) followed by
+// the back substitution L^H x = y.  Replaces inv(R) @ b (functions.py:465,530).  v1: one CTA per
+// frame, one thread per matrix row, DFMA.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chol_solve(SolveArgs A) {
+    const int jl = blockIdx.x, tid = threadIdx.x;
+    const int P = 2 * A.Mcols[jl];
+    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+    const int Pp = A.Pp;
+    __shared__ double2 Bk[kNb][kNb + 1];     // L[jb+c][kb+k]
+    __shared__ double2 D[kNb][kNb + 1];      // diagonal block
+    __shared__ double2 red[16][17];
+    __shared__ int bad;
+    extern __shared__ __align__(16) double2 xs[];   // [Pmax] solution
+    if (tid == 0) bad = 0;
+
+    for (int jb = 0; jb < P; jb += kNb) {
+        const int nbc = min(kNb, P - jb);
+        // phase 1: rows i in [jb, P]: W_i = R[i][jb..] - sum_kb L[i][kb..] L[jb..][kb..]^H
+        const int nrows = P + 1 - jb;
+        const int npass = (nrows + 255) / 256;
+        for (int pass = 0; pass < npass; pass++) {
+            const int i = jb + tid + pass * 256;
+            const bool live = i <= P;
+            double2 W[kNb];
+            if (live) {
+#pragma unroll
+                for (int c = 0; c < kNb; c++)
+                    W[c] = (c < nbc && jb + c <= i) ? RF[(size_t)i * Pp + jb + c] : make_double2(0.0, 0.0);
+            }
+            for (int kb = 0; kb < jb; kb += kNb) {
+                __syncthreads();
+                {
+                    const int c = tid >> 4, k = tid & 15;
+                    Bk[c][k] = (c < nbc) ? RF[(size_t)(jb + c) * Pp + kb + k] : make_double2(0.0, 0.0);
+                }
+                __syncthreads();
+                if (live) {
+                    const double2* Li = RF + (size_t)i * Pp + kb;
+#pragma unroll 4
+                    for (int k = 0; k < kNb; k++) {
+                        const double2 l = Li[k];
+#pragma unroll
+                        for (int c = 0; c < kNb; c++) cfms_conj_b(W[c], l, Bk[c][k]);
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int c = 0; c < kNb; c++) if (c < nbc && jb + c <= i) RF[(size_t)i * Pp + jb + c] = W[c];
+            }
+        }
+        __syncthreads();
+        // phase 2: factor the diagonal block
+        {
+            const int r = tid >> 4, c2 = tid & 15;
+            D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : make_double2(0.0, 0.0);
+            __syncthreads();
+            for (int c = 0; c < nbc; c++) {
+                if (tid == 0) {
+                    const double d = D[c][c].x;
+                    if (!(d > 0.0)) bad = 1;
+                    D[c][c] = make_double2(sqrt(d), 0.0);
+                }
+                __syncthreads();
+                if (c2 == c && r > c && r < nbc) {
+                    const double inv = 1.0 / D[c][c].x;
+                    D[r][c].x *= inv; D[r][c].y *= inv;
+                }
+                __syncthreads();
+                if (r > c && r < nbc && c2 > c && c2 <= r) cfms_conj_b(D[r][c2], D[r][c], D[c2][c]);
+                __syncthreads();
+            }
+            if (r < nbc && c2 <= r) RF[(size_t)(jb + r) * Pp + jb + c2] = D[r][c2];
+        }
+        __syncthreads();
+        // phase 3: rows below the diagonal block: W_i <- W_i L_jj^{-H}
+        {
+            const int nrows3 = P + 1 - (jb + nbc);
+            const int npass3 = (nrows3 + 255) / 256;
+            for (int pass = 0; pass < npass3; pass++) {
+                const int i = jb + nbc + tid + pass * 256;
+                if (i <= P) {
+                    double2 W[kNb];
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) W[c] = (c < nbc) ? RF[(size_t)i * Pp + jb + c] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) {
+                        if (c < nbc) {
+                            double2 v = W[c];
+#pragma unroll
+                            for (int cc = 0; cc < kNb; cc++) if (cc < c) cfms_conj_b(v, W[cc], D[c][cc]);
+                            const double inv = 1.0 / D[c][c].x;
+                            W[c] = make_double2(v.x * inv, v.y * inv);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) if (c < nbc) RF[(size_t)i * Pp + jb + c] = W[c];
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y
+    const int nblk = (P + kNb - 1) / kNb;
+    for (int b = nblk - 1; b >= 0; b--) {
+        const int jb = b * kNb, nbc = min(kNb, P - jb);
+        const int c = tid & 15, rr = tid >> 4;
+        double2 part = make_double2(0.0, 0.0);
+        if (c < nbc)
+            for (int i = jb + nbc + rr; i < P; i += 16) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
+        red[rr][c] = part;
+        __syncthreads();
+        if (tid < 32) {
+            double2 v = make_double2(0.0, 0.0);
+            if (tid < nbc) {
+                const double2 yq = RF[(size_t)P * Pp + jb + tid];
+                v = make_double2(yq.x, -yq.y);
+                for (int r2 = 0; r2 < 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
+            }
+            for (int cc = nbc - 1; cc >= 0; cc--) {
+                double2 xc = make_double2(0.0, 0.0);
+                if (tid == cc) {
+                    const double inv = 1.0 / RF[(size_t)(jb + cc) * Pp + jb + cc].x;
+                    xc = make_double2(v.x * inv, v.y * inv);
+                    xs[jb + cc] = xc;
+                }
+                xc.x = __shfl_sync(0xffffffffu, xc.x, cc);
+                xc.y = __shfl_sync(0xffffffffu, xc.y, cc);
+                if (tid < cc) {   // v -= conj(L[jb+cc][jb+tid]) * x_cc
+                    const double2 l = RF[(size_t)(jb + cc) * Pp + jb + tid];
+                    v.x -= l.x * xc.x + l.y * xc.y;
+                    v.y -= l.x * xc.y - l.y * xc.x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    double2* xo = A.x + (size_t)jl * A.Pmax;
+    for (int p = tid; p < P; p += 256) xo[p] = xs[p];
+    if (tid == 0 && bad && A.status) atomicAdd(&A.status[0], 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// frequency mismatch, acceptance test and knot write (functions.py:297-324)
+// ---------------------------------------------------------------------------------------
+__global__ void k_accept(AnaArgs A) {
+    const int jl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (jl >= A.nf) return;
+    const int g = A.t.alist[A.j0 + jl];
+    const int M = A.Mcols[jl], nz = (M - 1) / 2;
+    const int u = A.t.utt[g];
+    const double2* x = A.x + (size_t)jl * A.Pmax;
+    const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
+    const int64_t G = A.t.G;
+    double mx = 0.0;
+    for (int it = lane; it < nz; it += 32) mx = fmax(mx, hypot(x[it].x, x[it].y));
+    mx = warp_max(mx);
+    const double log_max = 20.0 * log10(mx) - 150.0;                       // functions.py:309
+    const double f0u = A.adapt == 0 ? A.t.f0[g] : A.t.f0stale[u];         // stale f0 for a >= 1 (Q1)
+    const double h = f0u / (double)(A.adapt + 1);                          // functions.py:310
+    const bool correct = f0u > A.t.f0min[u];                               // functions.py:321
+    if (lane == 0) A.k.a0[g] = x[2 * nz].x;                                // functions.py:303
+    const int64_t c = A.t.pos[g];
+    for (int it = lane; it < nz; it += 32) {
+        const int k = act[it];
+        const double2 a = x[it];
+        const double mag = hypot(a.x, a.y);
+        double df = 0.0;
+        if (A.adapt > 0) {
+            const double2 b = x[M + it];
+            df = (A.t.fs / kTwoPi) * ((a.x * b.y - a.y * b.x) / (mag * mag));   // functions.py:297
+        }
+        const bool ok = (20.0 * log10(mag) > log_max) && (fabs(df) < h);       // functions.py:315
+        if (ok) {
+            double f;
+            if (A.adapt == 0) f = (double)(k + 1) * f0u;                        // functions.py:320
+            else {
+                const double fc = A.fb[g] ? kFallbackFm : A.fm_cur[(int64_t)k * A.t.T + c];
+                f = correct ? fc + df : fc;                                     // functions.py:322-324
+            }
+            A.k.am[(int64_t)k * G + g] = mag;
+            A.k.ph[(int64_t)k * G + g] = atan2(a.y, a.x);
+            A.k.fm[(int64_t)k * G + g] = f;
+        }
+    }
+}
+
+size_t basis_smem_bytes(int Lp) {
+    return (size_t)Lp * 8 * 2 + (size_t)kBasisWarps * 2 * Lp * 8 + (size_t)kBasisWarps * 2 * Lp * 2;
+}
+
+}  // namespace
+
+AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max) {
+    AnaLayout l;
+    l.nnz_max = nnz_max;
+    l.Mmax = 2 * nnz_max + 1;
+    l.Pmax = 2 * l.Mmax;
+    l.Pp = (int32_t)align_up(l.Pmax, kNb);
+    l.Lp = (int32_t)align_up(2 * N_max + 1, 4);
+    int64_t o = 0;
+    l.off_fb = o;  o = align_up(o + G, 256);
+    l.off_M = o;   o = align_up(o + (int64_t)chunk * 4 * 2, 256);
+    l.off_act = o; o = align_up(o + (int64_t)chunk * nnz_max * 2, 256);
+    l.off_Ew = o;  o = align_up(o + (int64_t)chunk * l.Pmax * l.Lp * 16, 256);
+    l.off_R = o;   o = align_up(o + (int64_t)chunk * (l.Pmax + 1) * l.Pp * 16, 256);
+    l.off_x = o;   o = align_up(o + (int64_t)chunk * l.Pmax * 16, 256);
+    l.total = o;
+    return l;
+}
+
+int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st) {
+    const int Tt = (a.Pmax + 31) / 32;
+    dim3 grid(Tt * (Tt + 1) / 2, a.nf);
+    k_gram<<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
+    k_chol_solve<<<a.nf, 256, xs_bytes, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return EAQHM_OK;
+}
+
+extern "C" int64_t eaqhm_analysis_scratch_bytes(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max) {
+    if (G < 0 || chunk <= 0 || nnz_max <= 0 || N_max <= 0) return EAQHM_E_ARG;
+    return eaqhm_ana_layout(G, chunk, nnz_max, N_max).total;
+}
+
+extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const eaqhm_tracks* cur,
+                              const eaqhm_knots* knots, double* best_am, int32_t adapt, int32_t nnz_max,
+                              int32_t N_max, int32_t chunk, void* scratch, int64_t scratch_bytes,
+                              int32_t* status, void* stream) {
+    CHECK_ARG(tab && s && cur && knots && scratch && status);
+    CHECK_ARG(adapt >= 0 && nnz_max > 0 && N_max > 0 && chunk > 0);
+    CHECK_ARG(nnz_max <= 32767 && 2 * N_max + 1 <= 32767);
+    const AnaLayout l = eaqhm_ana_layout(tab->G, chunk, nnz_max, N_max);
+    CHECK_ARG(scratch_bytes >= l.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)scratch;
+    AnaArgs A;
+    A.t = *tab;
+    A.s = s;
+    A.am_cur = cur->am;
+    A.fm_cur = cur->fmc;
+    A.k = *knots;
+    A.best_am = best_am;
+    A.adapt = adapt;
+    A.nnz_max = l.nnz_max; A.Mmax = l.Mmax; A.Pmax = l.Pmax; A.Pp = l.Pp; A.Lp = l.Lp;
+    A.fb = base + l.off_fb;
+    A.Mcols = (int32_t*)(base + l.off_M);
+    A.Lrows = A.Mcols + chunk;
+    A.act = (int16_t*)(base + l.off_act);
+    A.Ew = (double2*)(base + l.off_Ew);
+    A.R = (double2*)(base + l.off_R);
+    A.x = (double2*)(base + l.off_x);
+    A.status = status;
+    if (tab->nA == 0) return EAQHM_OK;
+
+    const size_t smem = basis_smem_bytes(l.Lp);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_basis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_basis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    CHECK_ARG(smem <= 200 * 1024);
+
+    CUDA_TRY(cudaMemsetAsync(A.fb, 0, tab->G, st));
+    if (adapt > 0) {
+        A.j0 = 0; A.nf = tab->nA;
+        k_fallback_flags<<<(tab->nA * 32 + 255) / 256, 256, 0, st>>>(A);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (int j0 = 0; j0 < tab->nA; j0 += chunk) {
+        A.j0 = j0;
+        A.nf = min(chunk, tab->nA - j0);
+        k_active<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A);
+        CUDA_TRY(cudaGetLastError());
+        if (adapt == 0) k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A);
+        else k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A);
+        CUDA_TRY(cudaGetLastError());
+        SolveArgs S;
+        S.Ew = A.Ew; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
+        S.nf = A.nf; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
+        int rc = eaqhm_launch_gram_solve(S, st);
+        if (rc != EAQHM_OK) return rc;
+        k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return EAQHM_OK;
+}
+
+// ---- helper seams (host buffers) --------------------------------------------------------
+static int seam_solve(const double* s, int L, int M, const double* win, double fs, const double* am,
+                      const double* fm, const double* f0range, double* amp, double* slope) {
+    CHECK_ARG(s && win && amp && slope && L >= 3 && (L & 1) && M >= 1);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        eaqhm_set_error("no CUDA device: the eaQHM library has no CPU fallback");
+        return EAQHM_E_NODEVICE;
+    }
+    const int P = 2 * M, Pp = (int)align_up(P, kNb), Lp = (int)align_up(L, 4);
+    double *d_s = nullptr, *d_win = nullptr, *d_am = nullptr, *d_fm = nullptr, *d_f0 = nullptr;
+    double2 *d_Ew = nullptr, *d_R = nullptr, *d_x = nullptr;
+    int32_t* d_meta = nullptr;
+    int rc = EAQHM_OK;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc(&d_s, L * 8)); CUDA_TRY(cudaMalloc(&d_win, L * 8));
+        CUDA_TRY(cudaMemcpy(d_s, s, L * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_win, win, L * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d_Ew, (size_t)P * Lp * 16));
+        CUDA_TRY(cudaMalloc(&d_R, (size_t)(P + 1) * Pp * 16));
+        CUDA_TRY(cudaMemset(d_R, 0, (size_t)(P + 1) * Pp * 16));
+        CUDA_TRY(cudaMalloc(&d_x, (size_t)P * 16));
+        CUDA_TRY(cudaMalloc(&d_meta, 4 * sizeof(int32_t)));
+        const int32_t meta[4] = {M, L, 0, 0};
+        CUDA_TRY(cudaMemcpy(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice));
+        double2* Rb = d_R + (size_t)P * Pp;
+        if (f0range) {
+            CUDA_TRY(cudaMalloc(&d_f0, M * 8));
+            CUDA_TRY(cudaMemcpy(d_f0, f0range, M * 8, cudaMemcpyHostToDevice));
+            k_basis_harmonic_explicit<<<1, 256>>>(d_s, d_f0, d_win, L, M, fs, d_Ew, Lp, Rb);
+        } else {
+            CUDA_TRY(cudaMalloc(&d_am, (size_t)L * M * 8)); CUDA_TRY(cudaMalloc(&d_fm, (size_t)L * M * 8));
+            CUDA_TRY(cudaMemcpy(d_am, am, (size_t)L * M * 8, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(d_fm, fm, (size_t)L * M * 8, cudaMemcpyHostToDevice));
+            k_basis_explicit<<<1, 256, (size_t)8 * Lp * 8>>>(d_s, d_am, d_fm, d_win, L, M, fs, d_Ew, Lp, Rb);
+        }
+        CUDA_TRY(cudaGetLastError());
+        SolveArgs S;
+        S.Ew = d_Ew; S.R = d_R; S.x = d_x; S.Mcols = d_meta; S.Lrows = d_meta + 1;
+        S.nf = 1; S.Pmax = P; S.Pp = Pp; S.Lp = Lp; S.status = d_meta + 2;
+        int r2 = eaqhm_launch_gram_solve(S, 0);
+        if (r2 != EAQHM_OK) return r2;
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(amp, d_x, (size_t)M * 16, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(slope, d_x + M, (size_t)M * 16, cudaMemcpyDeviceToHost));
+        int32_t meta_out[4];
+        CUDA_TRY(cudaMemcpy(meta_out, d_meta, sizeof(meta_out), cudaMemcpyDeviceToHost));
+        if (meta_out[2] != 0) {
+            eaqhm_set_error("normal matrix is not positive definite");
+            return EAQHM_E_NOTPD;
+        }
+        return EAQHM_OK;
+    };
+    rc = body();
+    cudaFree(d_s); cudaFree(d_win); cudaFree(d_am); cudaFree(d_fm); cudaFree(d_f0);
+    cudaFree(d_Ew); cudaFree(d_R); cudaFree(d_x); cudaFree(d_meta);
+    return rc;
+}
+
+extern "C" int eaqhm_iqhmLS_complexamps(const double* s, int32_t L, const double* f0range, int32_t M,
+                                        const double* window, double fs, double* amp, double* slope) {
+    CHECK_ARG(f0range != nullptr);
+    return seam_solve(s, L, M, window, fs, nullptr, nullptr, f0range, amp, slope);
+}
+
+extern "C" int eaqhm_eaqhmLS_complexamps(const double* s, int32_t L, const double* am, const double* fm,
+                                         int32_t M, const double* window, double fs, double* amp, double* slope) {
+    CHECK_ARG(am != nullptr && fm != nullptr);
+    return seam_solve(s, L, M, window, fs, am, fm, nullptr, amp, slope);
+}

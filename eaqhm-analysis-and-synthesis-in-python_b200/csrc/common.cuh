@@ -1,0 +1,89 @@
+// Shared declarations of the eaQHM B200 library (internal; the public ABI is include/eaqhm_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/eaqhm_b200.h"
+
+#define EAQHM_VERSION 100
+
+static constexpr double kPi = 3.141592653589793;
+static constexpr double kTwoPi = 2.0 * 3.141592653589793;
+static constexpr double kAmEps = 10e-5;       // functions.py:517
+static constexpr double kFallbackFm = 140.0;  // functions.py:209
+static constexpr double kFallbackAm = 10e-4;  // functions.py:210
+
+void eaqhm_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            eaqhm_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,         \
+                            cudaGetErrorString(_e));                                     \
+            return EAQHM_E_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define CHECK_ARG(cond)                                                                  \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            eaqhm_set_error("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__);  \
+            return EAQHM_E_ARG;                                                          \
+        }                                                                                \
+    } while (0)
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---- complex helpers on double2 (x = re, y = im) ---------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc += conj(a) * b
+__device__ __forceinline__ void cfma_conj_a(double2& acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc -= a * conj(b)
+__device__ __forceinline__ void cfms_conj_b(double2& acc, double2 a, double2 b) {
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.y, b.x, acc.y); acc.y = fma(a.x, b.y, acc.y);
+}
+// acc += conj(a) * b  (same as cfma_conj_a; named for the back substitution)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- analysis stage internals (analysis.cu) -------------------------------------------
+struct AnaLayout {
+    int32_t nnz_max, Mmax, Pmax, Pp, Lp;   // Mmax = 2*nnz_max+1, Pmax = 2*Mmax, Pp = row pitch of R, Lp = pitch of Ew rows
+    int64_t off_fb, off_M, off_act, off_Ew, off_R, off_x, total;
+};
+AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max);
+
+// Solves `nf` already-built frames: Ew [nf][Pmax][Lp], Mcols[nf], Nhalf given per frame through the
+// tables (or Lfix>0 for the seams).  Fills R, runs the Cholesky solve, leaves x [nf][Pmax].
+struct SolveArgs {
+    const double2* Ew; double2* R; double2* x; const int32_t* Mcols;
+    const int32_t* Lrows;   // [nf] number of window samples per frame
+    int32_t nf, Pmax, Pp, Lp;
+    int32_t* status;
+};
+int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st);
+
+// spline helpers shared by interp.cu and synth.cu
+__device__ __forceinline__ double spline_eval(double y0, double y1, double m0, double m1, double h, double t1) {
+    // moment form of the cubic piece on [x_j, x_j + h] at offset t1 (functions.py:340,367 restated)
+    const double t0 = h - t1;
+    return (m0 * t0 * t0 * t0 + m1 * t1 * t1 * t1) / (6.0 * h) + (y0 / h - m0 * h / 6.0) * t0 +
+           (y1 / h - m1 * h / 6.0) * t1;
+}

@@ -1,0 +1,284 @@
+// Stage B of one eaQHM adaptation: interpolation of the per-frame parameters between frame
+// centres (reference: functions.py:337-383 and phase_integr_interpolation :537-575).
+#include "common.cuh"
+
+namespace {
+
+// forward-elimination factors of the constant tridiagonal (1,4,1) system of a uniform-knot cubic
+// spline: cp[0] = 1/4, cp[i] = 1/(4 - cp[i-1]); converges to 2 - sqrt(3) in < 40 steps.
+constexpr int kCpTab = 48;
+__constant__ double c_cp[kCpTab];
+
+__device__ __forceinline__ double cp_at(int i) { return c_cp[i < kCpTab ? i : kCpTab - 1]; }
+
+// Second derivatives ("moments") of the not-a-knot cubic spline through n >= 4 uniformly spaced
+// knots y[0..n) with spacing h (what interp1d(kind=3) == make_interp_spline(k=3) builds;
+// functions.py:340,367).  Sequential Thomas solve of the reduced system; m may alias nothing.
+__device__ void spline_moments(const double* __restrict__ y, double* __restrict__ m, int n, double h) {
+    auto rhs = [&](int j) {   // 6 (d_j - d_{j-1}) / h
+        const double d0 = (y[j] - y[j - 1]) / h, d1 = (y[j + 1] - y[j]) / h;
+        return 6.0 * (d1 - d0) / h;
+    };
+    const double m1 = rhs(1) / 6.0, mn2 = rhs(n - 2) / 6.0;
+    m[1] = m1;
+    m[n - 2] = mn2;
+    const int q0 = 2, q1 = n - 3;           // interior unknowns
+    if (q1 >= q0) {
+        double dprev = 0.0;
+        for (int q = q0; q <= q1; q++) {
+            double r = rhs(q);
+            if (q == q0) r -= m1;
+            if (q == q1) r -= mn2;
+            const double d = (q == q0) ? r * 0.25 : (r - dprev) * cp_at(q - q0);
+            m[q] = d;
+            dprev = d;
+        }
+        for (int q = q1 - 1; q >= q0; q--) m[q] = m[q] - cp_at(q - q0) * m[q + 1];
+    }
+    m[0] = 2.0 * m[1] - m[2];
+    m[n - 1] = 2.0 * m[n - 2] - m[n - 3];
+}
+
+// one thread per (harmonic k, utterance u): runs of >= 4 consecutive accepted frames get moments
+__global__ void k_run_moments(eaqhm_tables t, eaqhm_knots kn, double* mom) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= t.Kmax * t.U) return;
+    const int k = idx / t.U, u = idx % t.U;
+    if (!t.active[u]) return;
+    const int g0 = t.gfirst[u], n = t.gcount[u];
+    const double* am = kn.am + (int64_t)k * t.G + g0;
+    const double* fm = kn.fm + (int64_t)k * t.G + g0;
+    double* mo = mom + (int64_t)k * t.G + g0;
+    const double h = (double)t.step;
+    int i = 0;
+    while (i < n) {
+        if (am[i] == 0.0) { i++; continue; }
+        const int st = i;
+        while (i < n && am[i] != 0.0) i++;
+        if (i - st >= 4) spline_moments(fm + st, mo + st, i - st, h);
+    }
+}
+
+// DC spline through ALL frames of an utterance (functions.py:340)
+__global__ void k_a0_moments(eaqhm_tables t, const double* a0k, double* a0mom) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= t.U || !t.active[u]) return;
+    const int g0 = t.gfirst[u], n = t.gcount[u];
+    if (n >= 4) spline_moments(a0k + g0, a0mom + g0, n, (double)t.step);
+}
+
+// numpy.unwrap applied to one difference (period 2*pi), returned as the corrected difference
+__device__ __forceinline__ double unwrap_diff(double dd) {
+    double ddmod = fmod(dd + kPi, kTwoPi);
+    if (ddmod < 0.0) ddmod += kTwoPi;
+    ddmod -= kPi;
+    if (ddmod == -kPi && dd > 0.0) ddmod = kPi;
+    double corr = ddmod - dd;
+    if (fabs(dd) < kPi) corr = 0.0;
+    return dd + corr;
+}
+
+// cubic through 4 points in Lagrange form (short-run quirk Q4, functions.py:369-371)
+__device__ __forceinline__ double lagrange4(const double* X, const double* Y, double x) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double num = 1.0, den = 1.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j != i) { num *= (x - X[j]); den *= (X[i] - X[j]); }
+        acc += Y[i] * (num / den);
+    }
+    return acc;
+}
+
+// one thread per (harmonic k, frame g): owns samples [pos, pos+own) of the three dense tracks
+__global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, eaqhm_tracks tr, const double* mom,
+                                               double* fm_fin) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (g >= t.G) return;
+    const int u = t.utt[g];
+    if (!t.active[u]) return;
+    const int64_t G = t.G, T = t.T;
+    const int64_t x0 = t.pos[g];
+    const int own = t.own[g];
+    const int gl = g - t.gfirst[u], nu = t.gcount[u];
+    const double* amk = kn.am + (int64_t)k * G;
+    const double* fmk = kn.fm + (int64_t)k * G;
+    const double* phk = kn.ph + (int64_t)k * G;
+    double* am = tr.am + (int64_t)k * T;
+    double* ph = tr.ph + (int64_t)k * T;
+    double* fc = tr.fmc + (int64_t)k * T;
+    auto acc = [&](int d) { const int j = gl + d; return j >= 0 && j < nu && amk[g + d] != 0.0; };
+    const double y0 = amk[g];
+    const bool a0 = y0 != 0.0, has_prev = a0 && acc(-1), has_next = a0 && acc(1);
+
+    if (!has_next) {
+        // not a segment start: zero fill; an isolated accepted frame stays a one-sample impulse
+        // (functions.py:350-358 never interpolates it); the last knot of a run is written by its
+        // predecessor's thread.
+        for (int s = has_prev ? 1 : 0; s < own; s++) {
+            am[x0 + s] = 0.0; ph[x0 + s] = 0.0; fc[x0 + s] = 0.0;
+        }
+        if (a0 && !has_prev) { am[x0] = y0; ph[x0] = phk[g]; }
+        if (!has_prev) fm_fin[(int64_t)k * G + g] = a0 ? fmk[g] : 0.0;
+        return;
+    }
+
+    // segment g -> g+1 of a run
+    const int D = t.step;
+    const double h = (double)D;
+    const double y1 = amk[g + 1];
+    const bool next_last = !acc(2);
+    const int nback = has_prev ? (acc(-2) ? 2 : 1) : 0;
+    const int nfwd = next_last ? 0 : (acc(3) ? 2 : 1);
+    const bool shortrun = (nback + 2 + nfwd) < 4;
+    double LX[4], LY[4];
+    const double xl0 = (double)(x0 - t.ustart[u]);
+    if (shortrun) {
+        // knots: extra ones at local samples 0, step (functions.py:369) carrying whatever fm_recon
+        // holds there (the knot values of frames 0 and 1), then the run's own 2 or 3 knots
+        const int gs = g - nback;                  // first knot of the run
+        const int nrun = nback + 2 + nfwd;
+        const int64_t gu = t.gfirst[u];
+        int c = 0;
+        for (int e = 0; e < 4 - nrun; e++) { LX[c] = (double)(e * D); LY[c] = fmk[gu + e]; c++; }
+        for (int e = 0; e < nrun; e++) { LX[c] = (double)(t.pos[gs + e] - t.ustart[u]); LY[c] = fmk[gs + e]; c++; }
+    }
+    const double f0k = fmk[g], f1k = fmk[g + 1];
+    const double m0 = shortrun ? 0.0 : mom[(int64_t)k * G + g], m1 = shortrun ? 0.0 : mom[(int64_t)k * G + g + 1];
+    auto fm_at = [&](int s) {
+        return shortrun ? lagrange4(LX, LY, xl0 + (double)s) : spline_eval(f0k, f1k, m0, m1, h, (double)s);
+    };
+    const double wscale = kTwoPi / t.fs;            // functions.py:373: 2*pi/fs*fm_recon
+    // pass 1: end value of the running phase sum (functions.py:561-562)
+    double csum = 0.0;
+    for (int s = 0; s <= D; s++) csum += wscale * fm_at(s);
+    const double w0 = wscale * fm_at(0);
+    const double ph0 = phk[g], ph1 = phk[g + 1];
+    const double shift = ph0 - w0;
+    const double pend = csum + shift;
+    const double Mr = rint((pend - ph1) / kTwoPi);                              // functions.py:564
+    const double er = kPi * ((pend - ph1) - kTwoPi * Mr) / (double)(2 * D);    // functions.py:565
+    // pass 2: corrected phase, amplitude, new instantaneous frequency (functions.py:364,566-571,375)
+    const double slope = (y1 - y0) / h;
+    const double fscale = t.fs / kTwoPi;
+    double c2 = 0.0, e2 = 0.0, pprev = 0.0;
+    for (int s = 0; s <= D; s++) {
+        const double fv = fm_at(s);
+        c2 += wscale * fv;
+        e2 += sin((kPi * (double)s) / h) * er;
+        const double p = (c2 + shift) - e2;
+        if (s == 0) {
+            if (!has_prev) fc[x0] = fv;                                        // functions.py:375 first sample
+            fm_fin[(int64_t)k * G + g] = fv;
+        } else if (s < D) {
+            fc[x0 + s] = fscale * unwrap_diff(p - pprev);
+        }
+        if (s < D) {
+            am[x0 + s] = (s == 0) ? y0 : slope * (double)s + y0;
+            ph[x0 + s] = p;
+            pprev = p;
+        } else {
+            double pnext;
+            if (next_last) {
+                pnext = p;
+                am[x0 + D] = y1;
+                ph[x0 + D] = p;
+                fm_fin[(int64_t)k * G + g + 1] = fv;
+            } else {
+                // the next segment restarts from the measured phase (functions.py:562,571)
+                const double fn0 = shortrun ? fv : spline_eval(f1k, 0.0, m1, 0.0, h, 0.0);
+                const double wn0 = wscale * fn0;
+                pnext = wn0 + (ph1 - wn0);
+            }
+            fc[x0 + D] = fscale * unwrap_diff(pnext - pprev);
+        }
+    }
+}
+
+// dense-input version of the phase integration for the helper seam (functions.py:537-575)
+__global__ void k_phase_integr_dense(const double* fm, const double* phc, const int64_t* idx, int n, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int64_t i0 = idx[i], i1 = idx[i + 1], base = idx[0];
+    const int D = (int)(i1 - i0);
+    double csum = 0.0;
+    for (int s = 0; s <= D; s++) csum += fm[i0 + s];
+    const double shift = phc[i0] - fm[i0];
+    const double pend = csum + shift;
+    const double Mr = rint((pend - phc[i1]) / kTwoPi);
+    const double er = kPi * ((pend - phc[i1]) - kTwoPi * Mr) / (double)(2 * D);
+    double c2 = 0.0, e2 = 0.0;
+    for (int s = 0; s <= D; s++) {
+        c2 += fm[i0 + s];
+        e2 += sin((kPi * (double)s) / (double)D) * er;
+        if (s < D || i == n - 2) out[i0 - base + s] = (c2 + shift) - e2;
+    }
+}
+
+bool g_cp_ready = false;
+int ensure_cp_table() {
+    if (g_cp_ready) return EAQHM_OK;
+    double cp[kCpTab];
+    cp[0] = 0.25;
+    for (int i = 1; i < kCpTab; i++) cp[i] = 1.0 / (4.0 - cp[i - 1]);
+    CUDA_TRY(cudaMemcpyToSymbol(c_cp, cp, sizeof(cp)));
+    g_cp_ready = true;
+    return EAQHM_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t eaqhm_interp_work_bytes(int32_t G, int32_t Kmax) {
+    if (G < 0 || Kmax <= 0) return EAQHM_E_ARG;
+    return align_up((int64_t)G * Kmax * 8, 256);
+}
+
+extern "C" int eaqhm_interpolate(const eaqhm_tables* tab, const eaqhm_knots* knots, const eaqhm_tracks* out,
+                                 double* fm_fin, double* a0mom, void* work, int64_t work_bytes, void* stream) {
+    CHECK_ARG(tab && knots && out && fm_fin && a0mom && work);
+    CHECK_ARG(work_bytes >= eaqhm_interp_work_bytes(tab->G, tab->Kmax));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_cp_table();
+    if (rc != EAQHM_OK) return rc;
+    double* mom = (double*)work;
+    const int nt = tab->Kmax * tab->U;
+    k_run_moments<<<(nt + 31) / 32, 32, 0, st>>>(*tab, *knots, mom);
+    CUDA_TRY(cudaGetLastError());
+    k_a0_moments<<<(tab->U + 31) / 32, 32, 0, st>>>(*tab, knots->a0, a0mom);
+    CUDA_TRY(cudaGetLastError());
+    dim3 grid((tab->G + 127) / 128, tab->Kmax);
+    k_interp<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin);
+    CUDA_TRY(cudaGetLastError());
+    return EAQHM_OK;
+}
+
+extern "C" int eaqhm_phase_integr_interpolation(const double* fm_recon, const double* ph_recon, int64_t length,
+                                                const int64_t* indices, int32_t n, double* out) {
+    CHECK_ARG(fm_recon && ph_recon && indices && out && n >= 2 && length > 0);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        eaqhm_set_error("no CUDA device: the eaQHM library has no CPU fallback");
+        return EAQHM_E_NODEVICE;
+    }
+    for (int i = 0; i < n; i++) CHECK_ARG(indices[i] >= 0 && indices[i] < length && (i == 0 || indices[i] > indices[i - 1]));
+    const int64_t nout = indices[n - 1] - indices[0] + 1;
+    double *d_fm = nullptr, *d_ph = nullptr, *d_out = nullptr;
+    int64_t* d_idx = nullptr;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc(&d_fm, length * 8)); CUDA_TRY(cudaMalloc(&d_ph, length * 8));
+        CUDA_TRY(cudaMalloc(&d_out, nout * 8)); CUDA_TRY(cudaMalloc(&d_idx, (size_t)n * 8));
+        CUDA_TRY(cudaMemcpy(d_fm, fm_recon, length * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_ph, ph_recon, length * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_idx, indices, (size_t)n * 8, cudaMemcpyHostToDevice));
+        k_phase_integr_dense<<<(n - 1 + 127) / 128, 128>>>(d_fm, d_ph, d_idx, n, d_out);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(out, d_out, nout * 8, cudaMemcpyDeviceToHost));
+        return EAQHM_OK;
+    };
+    const int rc = body();
+    cudaFree(d_fm); cudaFree(d_ph); cudaFree(d_out); cudaFree(d_idx);
+    return rc;
+}

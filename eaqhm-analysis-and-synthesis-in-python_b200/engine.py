@@ -1,0 +1,227 @@
+"""Adaptation loop of the eaQHM hot path on one GPU (functions.py:163-402).
+
+Python orchestrates; every numeric stage is a call through the C ABI of
+libeaqhm_b200.so (include/eaqhm_b200.h) on device buffers owned by torch tensors.
+A batch of utterances (or the frame-range shards of one long signal) is laid out on
+one concatenated sample axis; utterances adapt in lockstep and drop out of the
+batch when their SRER stops improving (functions.py:394-396).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from .host import FrameTables
+
+
+@dataclass
+class Utterance:
+    """Array-level inputs of the hot path for one signal."""
+    s: np.ndarray                   # (length,) float64 in [-1,1)
+    fs: int
+    f0s: np.ndarray                 # (n5,3) rows [t, f0, strength] on the 5 ms grid (functions.py:113)
+    voiced5: np.ndarray             # (n5',) isVoiced per 5 ms frame after the mode handling (functions.py:127-146)
+    frame_step: int                 # samples between 5 ms frames (functions.py:642)
+    f0min: float                    # lower pitch limit (functions.py:95-109)
+    Kmax: int                       # functions.py:117-120
+    det_part: np.ndarray = None     # SRER target (functions.py:138,146); default s
+
+
+@dataclass
+class Result:
+    s_recon: np.ndarray
+    SRER: list
+    ti: np.ndarray                  # 0-based centre of every frame
+    isSpeech: np.ndarray
+    isVoiced: np.ndarray
+    a0: np.ndarray                  # (No_ti,)
+    am: np.ndarray                  # (No_ti,Kmax)
+    fm: np.ndarray
+    ph: np.ndarray
+    n_adapt_best: int = 0
+    stats: dict = field(default_factory=dict)
+
+
+def _dev(a, dtype, device):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device, non_blocking=False)
+
+
+class Engine:
+    """Holds the device buffers of one batch and runs the adaptation loop."""
+
+    def __init__(self, utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32,
+                 device="cuda", chunk=None, scratch_budget_bytes=6 << 30):
+        if not torch.cuda.is_available():
+            raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
+        self.L = _lib.lib()
+        self.device = torch.device(device)
+        self.utts = list(utterances)
+        U = len(self.utts)
+        if U == 0:
+            raise ValueError("empty batch")
+        fs = self.utts[0].fs
+        if any(u.fs != fs for u in self.utts):
+            raise ValueError("all utterances of a batch must share the sample rate")
+        self.fs, self.step, self.maxAdpt = fs, int(step), int(maxAdpt)
+        self.ft = [FrameTables(len(u.s), fs, u.f0s, u.voiced5, u.frame_step, u.Kmax, step, pitchPeriods,
+                               analysisWindow) for u in self.utts]
+        self.U = U
+        self.Kmax = max(u.Kmax for u in self.utts)
+        lens = np.array([f.length for f in self.ft], np.int64)
+        cnts = np.array([f.No_ti for f in self.ft], np.int32)
+        self.ustart = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+        self.gfirst = np.concatenate(([0], np.cumsum(cnts)[:-1])).astype(np.int32)
+        self.T, self.G = int(lens.sum()), int(cnts.sum())
+        self.lens, self.cnts = lens, cnts
+        d = self.device
+        cat = np.concatenate
+        self.t_pos = _dev(cat([self.ustart[i] + f.ti0 for i, f in enumerate(self.ft)]), np.int64, d)
+        self.t_own = _dev(cat([f.own for f in self.ft]), np.int32, d)
+        self.t_utt = _dev(cat([np.full(f.No_ti, i) for i, f in enumerate(self.ft)]), np.int32, d)
+        self.t_N = _dev(cat([f.N for f in self.ft]), np.int32, d)
+        self.t_K0 = _dev(cat([f.K0 for f in self.ft]), np.int32, d)
+        self.t_f0 = _dev(cat([f.f0 for f in self.ft]), np.float64, d)
+        self.t_ustart = _dev(self.ustart, np.int64, d)
+        self.t_ulen = _dev(lens, np.int64, d)
+        self.t_gfirst = _dev(self.gfirst, np.int32, d)
+        self.t_gcount = _dev(cnts, np.int32, d)
+        self.t_f0stale = _dev([f.f0stale for f in self.ft], np.float64, d)
+        self.t_f0min = _dev([float(u.f0min) for u in self.utts], np.float64, d)
+        self.t_active = torch.ones(U, dtype=torch.uint8, device=d)
+        self.alists = [self.gfirst[i] + np.flatnonzero(f.analysed).astype(np.int32) for i, f in enumerate(self.ft)]
+        self.t_alist = torch.empty(max(1, sum(len(a) for a in self.alists)), dtype=torch.int32, device=d)
+        self.s = _dev(cat([np.asarray(u.s, float).reshape(-1) for u in self.utts]), np.float64, d)
+        dets = [np.asarray(u.s if u.det_part is None else u.det_part, float).reshape(-1) for u in self.utts]
+        self.det = _dev(cat(dets), np.float64, d)
+        self.std_det = np.array([np.std(x) for x in dets])                   # functions.py:161
+        self.nnz_max = int(max(1, max(int(f.K0.max()) for f in self.ft)))
+        self.N_max = int(max(1, max(int(f.N.max()) for f in self.ft)))
+        K, T, G = self.Kmax, self.T, self.G
+        f64 = dict(dtype=torch.float64, device=d)
+        self.tr = [torch.zeros(K * T, **f64) for _ in range(3)]              # am, ph, fmc  [Kmax][T]
+        self.kn = [torch.zeros(K * G, **f64) for _ in range(3)] + [torch.zeros(G, **f64)]    # am, ph, fm, a0
+        self.best = [torch.zeros(K * G, **f64) for _ in range(3)] + [torch.zeros(G, **f64)]
+        self.fm_fin = torch.zeros(K * G, **f64)
+        self.a0mom = torch.zeros(G, **f64)
+        self.s_hat = torch.zeros(T, **f64)
+        self.s_best = torch.zeros(T, **f64)
+        self.var = torch.zeros(U, **f64)
+        self.improved = torch.zeros(U, dtype=torch.uint8, device=d)
+        self.status = torch.zeros(2, dtype=torch.int32, device=d)
+        nA = int(self.t_alist.numel())
+        if chunk is None:
+            per_frame = self.L.eaqhm_analysis_scratch_bytes(0, 1, self.nnz_max, self.N_max)
+            chunk = int(max(1, min(nA, scratch_budget_bytes // max(1, per_frame))))
+        self.chunk = int(chunk)
+        nb = self.L.eaqhm_analysis_scratch_bytes(G, self.chunk, self.nnz_max, self.N_max)
+        self.scratch = torch.empty(nb, dtype=torch.uint8, device=d)
+        self.iwork = torch.empty(self.L.eaqhm_interp_work_bytes(G, K), dtype=torch.uint8, device=d)
+        self.swork = torch.empty(self.L.eaqhm_synth_work_bytes(int(lens.max()), U), dtype=torch.uint8, device=d)
+        self.tab = _lib.Tables()
+        t = self.tab
+        t.T, t.maxlen, t.G, t.U, t.Kmax, t.step, t.fs = T, int(lens.max()), G, U, K, self.step, float(fs)
+        for name in ("pos", "own", "utt", "N", "K0", "f0", "ustart", "ulen", "gfirst", "gcount", "f0stale",
+                     "f0min", "active", "alist"):
+            setattr(t, name, getattr(self, "t_" + name).data_ptr())
+        t.nA = 0
+        self.c_tr = _lib.Tracks(*[x.data_ptr() for x in self.tr])
+        self.c_kn = _lib.Knots(*[x.data_ptr() for x in self.kn])
+        self.c_best = _lib.Knots(*[x.data_ptr() for x in self.best])
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_active(self, active):
+        act = np.asarray(active, bool)
+        self.t_active.copy_(torch.from_numpy(act.astype(np.uint8)))
+        al = [self.alists[i] for i in range(self.U) if act[i]]
+        al = np.concatenate(al) if al else np.zeros(0, np.int32)
+        if len(al):
+            self.t_alist[:len(al)].copy_(torch.from_numpy(al))
+        self.tab.nA = int(len(al))
+        return int(len(al))
+
+    def analysis(self, a):
+        """Stage A (functions.py:176-329)."""
+        for x in self.kn:
+            x.zero_()
+        _lib.check(self.L.eaqhm_analysis(C.byref(self.tab), self.s.data_ptr(), C.byref(self.c_tr), C.byref(self.c_kn),
+                                         self.best[0].data_ptr(), a, self.nnz_max, self.N_max, self.chunk,
+                                         self.scratch.data_ptr(), self.scratch.numel(), self.status.data_ptr(),
+                                         self._stream()))
+
+    def interpolate(self):
+        """Stage B (functions.py:337-383)."""
+        _lib.check(self.L.eaqhm_interpolate(C.byref(self.tab), C.byref(self.c_kn), C.byref(self.c_tr),
+                                            self.fm_fin.data_ptr(), self.a0mom.data_ptr(), self.iwork.data_ptr(),
+                                            self.iwork.numel(), self._stream()))
+
+    def synthesize(self):
+        """Stage C (functions.py:385-388); returns the residual variance per utterance (device tensor)."""
+        _lib.check(self.L.eaqhm_synthesize(C.byref(self.tab), C.byref(self.c_tr), self.kn[3].data_ptr(),
+                                           self.a0mom.data_ptr(), self.det.data_ptr(), self.s_hat.data_ptr(),
+                                           self.var.data_ptr(), self.swork.data_ptr(), self.swork.numel(),
+                                           self._stream()))
+        return self.var
+
+    def snapshot(self, improved):
+        self.improved.copy_(torch.from_numpy(np.asarray(improved, bool).astype(np.uint8)))
+        _lib.check(self.L.eaqhm_snapshot(C.byref(self.tab), self.improved.data_ptr(), C.byref(self.c_tr),
+                                         C.byref(self.c_kn), self.fm_fin.data_ptr(), self.a0mom.data_ptr(),
+                                         self.s_hat.data_ptr(), self.s_best.data_ptr(), C.byref(self.c_best),
+                                         self._stream()))
+
+    # ------------------------------------------------------------------------------
+    def run(self, on_adaptation=None):
+        """The adaptation loop (functions.py:163-402).  Returns one Result per utterance."""
+        U = self.U
+        active = np.ones(U, bool)
+        SRER = [[] for _ in range(U)]
+        best_a = np.zeros(U, int)
+        frames_solved = 0
+        for a in range(self.maxAdpt + 1):
+            nA = self.set_active(active)
+            frames_solved += nA
+            self.analysis(a)
+            self.interpolate()
+            var = self.synthesize().cpu().numpy()                           # the one host sync per adaptation
+            improved = np.zeros(U, bool)
+            with np.errstate(all="ignore"):
+                for u in np.flatnonzero(active):
+                    srer = 20 * np.log10(self.std_det[u] / np.sqrt(var[u]))  # functions.py:388
+                    SRER[u].append(srer)
+                    if a != 0 and srer <= SRER[u][a - 1]:                   # functions.py:394-396
+                        active[u] = False
+                    else:
+                        improved[u] = True
+                        best_a[u] = a
+            self.snapshot(improved)                                         # functions.py:397-402
+            if on_adaptation is not None:
+                on_adaptation(a, SRER)
+            if not active.any():
+                break
+        return self.results(SRER, best_a, frames_solved)
+
+    def results(self, SRER, best_a, frames_solved=0):
+        K, G = self.Kmax, self.G
+        s_best = self.s_best.cpu().numpy()
+        b_am, b_ph, b_fm = [x.view(K, G).cpu().numpy() for x in self.best[:3]]
+        b_a0 = self.best[3].cpu().numpy()
+        status = self.status.cpu().numpy()
+        out = []
+        for i, (u, f) in enumerate(zip(self.utts, self.ft)):
+            g0, n = self.gfirst[i], f.No_ti
+            sl = slice(g0, g0 + n)
+            ku = u.Kmax
+            out.append(Result(
+                s_recon=s_best[self.ustart[i]:self.ustart[i] + f.length].copy(), SRER=list(SRER[i]), ti=f.ti0.copy(),
+                isSpeech=f.isSpeech.copy(), isVoiced=f.analysed.copy(), a0=b_a0[sl].copy(),
+                am=b_am[:ku, sl].T.copy(), fm=b_fm[:ku, sl].T.copy(), ph=b_ph[:ku, sl].T.copy(),
+                n_adapt_best=int(best_a[i]),
+                stats=dict(not_pd_frames=int(status[0]), fallback_frames=int(status[1]),
+                           frames_solved=int(frames_solved))))
+        return out

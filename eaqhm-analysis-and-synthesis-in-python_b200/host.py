@@ -1,0 +1,106 @@
+"""Host-side setup of the hot path: the O(No_ti) integer/flag logic of functions.py:95-161
+and :176-194 (gender limits, Kmax, full-waveform override, voiced-only SRER target, frame
+grid, gating, per-frame f0 / K / window length).  Plain numpy; no device work.
+"""
+import numpy as np
+
+NORMALIZE = 32768      # misc.py:13
+
+
+def gender_limits(gender):
+    """functions.py:95-109."""
+    if isinstance(gender, tuple):
+        return gender[0], gender[1]
+    if gender == "male":
+        return 70, 180
+    if gender == "female":
+        return 160, 300
+    if gender == "child":
+        return 300, 600
+    return 70, 500
+
+
+def harmonic_capacity(fs, f0s, partials=0):
+    """Fmax and Kmax (functions.py:115-120)."""
+    Fmax = int(fs / 2 - 200)
+    if partials > 0:
+        return Fmax, int(partials)
+    return Fmax, int(round(Fmax / min(f0s[:, 1])) + 10)
+
+
+def full_waveform_flags(speech5, voiced5, length, frame_step, analysisWindowSamples):
+    """functions.py:140-145: inside the analysable span every 5 ms frame becomes speech+voiced."""
+    speech5 = np.array(speech5, bool)
+    voiced5 = np.array(voiced5, bool)
+    ti5 = np.arange(1, length, frame_step)[:len(speech5)]
+    inside = (ti5 > analysisWindowSamples / 2) & (ti5 < length - analysisWindowSamples / 2)
+    first = inside & speech5 & ~voiced5
+    voiced5 = voiced5 | first
+    second = inside & ~speech5 & ~voiced5
+    speech5 = speech5 | second
+    voiced5 = voiced5 | second
+    return speech5, voiced5
+
+
+def voiced_only_target(s, speech5, voiced5, frame_step):
+    """functions.py:127-138: SRER target that keeps only the voiced regions (quirk Q9: a voiced
+    region that reaches the last 5 ms frame is never copied)."""
+    s = np.asarray(s, float).reshape(-1)
+    ss = np.zeros(len(s))
+    ti5 = np.arange(1, len(s), frame_step)
+    sp = []
+    for j in range(len(speech5)):
+        if speech5[j] and voiced5[j]:
+            sp.append(ti5[j])
+        elif sp:
+            lo, hi = sp[0] - frame_step, sp[-1] + frame_step + 1
+            idx = np.arange(lo, hi)          # negative indices wrap like the reference's fancy index
+            ss[idx] = s[idx]
+            sp = []
+    return ss
+
+
+class FrameTables:
+    """Per-frame quantities of one utterance (functions.py:148-157,176-194)."""
+
+    def __init__(self, length, fs, f0s, voiced5, frame_step, Kmax, step=15, pitchPeriods=3,
+                 analysisWindow=32):
+        if analysisWindow * step < 2 * step:
+            raise ValueError("analysisWindow*step must be at least 2*step (the reference's run detection "
+                             "and short-run spline assume no frame is analysed at samples 0 and step)")
+        f0s = np.asarray(f0s, float)
+        voiced5 = np.asarray(voiced5, bool)
+        self.length, self.step = int(length), int(step)
+        Fmax = int(fs / 2 - 200)
+        ti = np.arange(1, length, step)                                   # functions.py:148 (1-based)
+        self.No_ti = len(ti)
+        if self.No_ti < 4:
+            raise ValueError("signal too short: the DC cubic spline needs at least 4 frames (functions.py:340)")
+        framei = ti / frame_step                                          # functions.py:155
+        fi = framei.astype(int)
+        dec = framei - fi
+        aw = analysisWindow * step
+        self.isSpeech = (ti > aw) & (ti < length - aw)                    # functions.py:180
+        nv = len(voiced5)
+        self.analysed = self.isSpeech & voiced5[(fi - 1) % nv] & voiced5[np.minimum(fi, nv - 1)]   # :181
+        idx = np.flatnonzero(self.analysed)
+        self.f0 = np.zeros(self.No_ti)
+        self.K0 = np.zeros(self.No_ti, np.int32)
+        self.N = np.zeros(self.No_ti, np.int32)
+        if len(idx):
+            f0 = (1 - dec[idx]) * f0s[fi[idx] - 1, 1] + dec[idx] * f0s[fi[idx], 1]      # functions.py:185
+            if not np.all(np.isfinite(f0)) or np.any(f0 <= 0):
+                raise ValueError("f0 track has non-finite or non-positive values on analysed frames")
+            self.f0[idx] = f0
+            self.K0[idx] = np.minimum(Kmax, (Fmax / f0).astype(int))                    # functions.py:187
+            self.N[idx] = np.maximum(120, np.rint((pitchPeriods / 2) * (fs / f0))).astype(np.int32)   # :191
+            c = ti[idx] - 1
+            if np.any(c + self.N[idx] >= length):
+                raise IndexError("analysis window runs past the end of the signal "
+                                 "(the reference raises IndexError at functions.py:196)")
+            if np.any(self.K0[idx] < 1):
+                raise ValueError("f0 above Fmax: no harmonic fits")
+        self.ti0 = ti - 1                                                 # 0-based centres (functions.py:325)
+        self.f0stale = float(self.f0[idx[-1]]) if len(idx) else 0.0       # quirk Q1
+        self.own = np.full(self.No_ti, step, np.int32)
+        self.own[-1] = length - self.ti0[-1]
