@@ -72,10 +72,15 @@ _SIGNATURES = {
     "eaqhm_version": (C.c_int, []),
     "eaqhm_last_error": (C.c_char_p, []),
     "eaqhm_device_count": (C.c_int, []),
+    "eaqhm_profile_enable": (C.c_int, [C.c_int]),
+    "eaqhm_profile_reset": (C.c_int, []),
+    "eaqhm_profile_classes": (C.c_int, []),
+    "eaqhm_profile_name": (C.c_char_p, [C.c_int]),
+    "eaqhm_profile_read": (C.c_int, [c_f64p, c_i64p, C.c_int32]),
     "eaqhm_analysis_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "eaqhm_analysis": (C.c_int, [C.POINTER(Tables), C.c_void_p, C.POINTER(Tracks), C.POINTER(Knots), C.c_void_p,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
-                                 C.c_void_p]),
+                                 C.c_void_p, C.c_void_p]),
     "eaqhm_interp_work_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "eaqhm_interpolate": (C.c_int, [C.POINTER(Tables), C.POINTER(Knots), C.POINTER(Tracks), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_void_p]),
@@ -114,3 +119,14 @@ def lib():
 def check(rc):
     if rc != 0:
         raise EaqhmError("eaqhm error %d: %s" % (rc, lib().eaqhm_last_error().decode()))
+
+
+def profile_read():
+    """{kernel class: (milliseconds, launches)} accumulated since the last profile_reset()."""
+    import numpy as np
+    L = lib()
+    n = L.eaqhm_profile_classes()
+    ms = np.zeros(n)
+    cnt = np.zeros(n, np.int64)
+    check(L.eaqhm_profile_read(ms.ctypes.data_as(c_f64p), cnt.ctypes.data_as(c_i64p), n))
+    return {L.eaqhm_profile_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -1,0 +1,109 @@
+"""Drop-in entry points with the reference's call signature (functions.py:35-37,418).
+
+``eaQHMAnalysisAndSynthesis`` keeps the reference's arguments and its four return values
+(s_recon, SRER, DetComponents, endTime).  Host preprocessing (wav read, optional high-pass,
+SWIPE' f0, 5 ms resampling, speech/voiced flags) stays on the CPU (``preprocess.py``); the
+adaptation loop (functions.py:163-402) runs on the GPU through ``engine.Engine``.
+"""
+from time import time, strftime, gmtime
+
+import numpy as np
+
+from . import host
+from .engine import Engine, Utterance
+from .structs import Deterministic
+
+
+def _array_by_index(idx, values):
+    """misc.py:65-93 (arrayByIndex) as the packing step uses it: an object array, dense up to the
+    last index, holding one-element float arrays at ``idx`` and int 0 elsewhere (quirk Q8)."""
+    if len(idx) == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # misc.py:61-62 via functions.py:409
+    r = np.zeros(int(idx[-1]) + 1, dtype=object)
+    for i, v in zip(idx, values):
+        r[int(i)] = np.array([v])
+    return r
+
+
+def pack_det_components(res):
+    """functions.py:151,325-329,404-411: list of Deterministic records, one per frame."""
+    out = []
+    for i in range(len(res.ti)):
+        d = Deterministic(ti=int(res.ti[i]), isSpeech=bool(res.isSpeech[i]), isVoiced=bool(res.isVoiced[i]))
+        if d.isVoiced:
+            nz = np.flatnonzero(res.am[i])
+            d.a0 = res.a0[i]
+            d.amplitudes = _array_by_index(nz, res.am[i, nz])
+            d.frange = _array_by_index(nz, res.fm[i, nz])
+            d.pk = _array_by_index(nz, res.ph[i, nz])
+        out.append(d)
+    return out
+
+
+def make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, analysisWindow=32,
+                   fullWaveform=True, partials=0):
+    """Mode handling of functions.py:95-146 on array inputs -> engine.Utterance."""
+    s = np.asarray(s, float).reshape(-1)
+    f0min, _ = host.gender_limits(gender)
+    _, Kmax = host.harmonic_capacity(fs, np.asarray(f0s, float), partials)
+    if fullWaveform:
+        speech5, voiced5 = host.full_waveform_flags(speech5, voiced5, len(s), frame_step, analysisWindow * step)
+        det = None
+    else:
+        det = host.voiced_only_target(s, speech5, voiced5, frame_step)
+    return Utterance(s=s, fs=int(fs), f0s=np.asarray(f0s, float), voiced5=np.asarray(voiced5, bool),
+                     frame_step=int(frame_step), f0min=float(f0min), Kmax=int(Kmax), det_part=det)
+
+
+def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10,
+                   pitchPeriods=3, analysisWindow=32, fullWaveform=True, partials=0, on_adaptation=None):
+    """The hot path on array-level inputs; returns an engine.Result."""
+    u = make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender, step, analysisWindow, fullWaveform, partials)
+    eng = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow)
+    return eng.run(on_adaptation)[0]
+
+
+def analyze_batch(utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32, **engine_kw):
+    """A batch of engine.Utterance on one GPU; returns a list of engine.Result."""
+    eng = Engine(utterances, step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow,
+                 **engine_kw)
+    return eng.run()
+
+
+def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', step: int = 15,
+                              maxAdpt: int = 10, pitchPeriods: int = 3, analysisWindow: int = 32,
+                              fullWaveform: bool = True, fc: int = 0, partials: int = 0,
+                              printPrompts: bool = True, loadingScreen: bool = True, *, f0s=None, frames=None):
+    """Same call signature and return values as the reference (functions.py:35-81,418).
+
+    Keyword-only extensions: ``f0s`` ((n,3) [t,f0,strength] track, replaces SWIPE') and ``frames``
+    ((speech5, voiced5, frame_step), replaces voicedUnvoicedFrames) let a caller supply the
+    host preprocessing results; ``loadingScreen`` is accepted and ignored (no per-frame loop).
+    """
+    from . import preprocess
+    startTime = time()
+    fs, s = preprocess.read_wav(speechFile)                                   # functions.py:86-87
+    if fc > 0:
+        s = preprocess.ellipFilter(s, fs, fc)                                 # functions.py:90-91
+    f0min, f0max = host.gender_limits(gender)
+    if f0s is None:
+        f0s = preprocess.swipep(s, fs, [f0min, f0max])                        # functions.py:111
+    f0s = preprocess.getLinear(np.asarray(f0s, float), np.arange(0, len(s) - 1, round(fs * 5 / 1000)) / fs)   # :113
+    if frames is None:
+        speech5, voiced5, frame_step = preprocess.voicedUnvoicedFrames(s, fs, gender)   # functions.py:125
+    else:
+        speech5, voiced5, frame_step = frames
+
+    def prompt(a, SRER):
+        if printPrompts:
+            print('---- Adaptation No. {} ----\n'.format(a))
+            print('\nSRER: {} dB in Adaptation No: {}'.format(SRER[0][a], a))
+
+    res = analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender, step, maxAdpt, pitchPeriods,
+                         analysisWindow, fullWaveform, partials, on_adaptation=prompt)
+    det = pack_det_components(res)
+    endTime = time() - startTime
+    if printPrompts:
+        print('Signal adapted to {} dB SRER'.format(round(max(res.SRER), 6)))
+        print('Total Time: {}\n\n'.format(strftime("%H:%M:%S", gmtime(endTime))))
+    return res.s_recon, res.SRER, det, endTime

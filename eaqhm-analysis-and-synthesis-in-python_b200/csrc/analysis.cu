@@ -19,6 +19,7 @@ struct AnaArgs {
     int32_t adapt;
     int32_t j0, nf;                 // chunk of the analysed list: [j0, j0+nf)
     int32_t nnz_max, Mmax, Pmax, Pp, Lp;
+    int32_t nwb;                    // warps of the basis kernel that own a column buffer (smem bound for long windows)
     uint8_t* fb;                    // [G] fallback flags of this adaptation
     int32_t* Mcols;                 // [chunk] columns of E2 per frame (2*nnz+1)
     int32_t* Lrows;                 // [chunk] window samples per frame
@@ -27,6 +28,7 @@ struct AnaArgs {
     double2* R;                     // [chunk][Pmax+1][Pp]   (row P = conj(rhs))
     double2* x;                     // [chunk][Pmax]
     int32_t* status;
+    double* flop_stats;             // [3] += algorithmic flops of the Gram / Cholesky / basis+rhs (may be null)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -82,6 +84,12 @@ __global__ void k_active(AnaArgs A) {
     if (lane == 0) {
         A.Mcols[jl] = 2 * count + 1;
         A.Lrows[jl] = 2 * A.t.N[g] + 1;
+        if (A.flop_stats) {   // structure-aware minimum work of this frame
+            const double M = 2.0 * count + 1.0, L = 2.0 * A.t.N[g] + 1.0, P = 2.0 * M;
+            atomicAdd(&A.flop_stats[0], 12.0 * L * M * M);
+            atomicAdd(&A.flop_stats[1], (4.0 / 3.0) * P * P * P + 8.0 * P * P);
+            atomicAdd(&A.flop_stats[2], 16.0 * L * M);
+        }
     }
 }
 
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     double* ws = w + A.Lp;
     double* fmw = ws + A.Lp + (size_t)warp * 2 * A.Lp;
     double* amw = fmw + A.Lp;
-    int16_t* prv = reinterpret_cast<int16_t*>(ws + A.Lp + (size_t)kBasisWarps * 2 * A.Lp) + (size_t)warp * 2 * A.Lp;
+    int16_t* prv = reinterpret_cast<int16_t*>(ws + A.Lp + (size_t)A.nwb * 2 * A.Lp) + (size_t)warp * 2 * A.Lp;
     int16_t* nxt = prv + A.Lp;
 
     // analysis window (numpy.blackman / numpy.hamming, functions.py:194,200) and windowed signal
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
     const double f0 = A.t.f0[g];
 
-    for (int it = warp; it <= nz; it += kBasisWarps) {
+    for (int it = warp; it <= nz && warp < A.nwb; it += A.nwb) {
         if (it == nz) {   // DC column: E2 = 1 (fm = 0, am = 0 -> (eps+0)/(0+eps) = 1)
             double s0 = 0.0, s1 = 0.0;
             double2* e0 = EwF + (size_t)(2 * nz) * A.Lp;
@@ -573,8 +581,8 @@ __global__ void k_accept(AnaArgs A) {
     }
 }
 
-size_t basis_smem_bytes(int Lp) {
-    return (size_t)Lp * 8 * 2 + (size_t)kBasisWarps * 2 * Lp * 8 + (size_t)kBasisWarps * 2 * Lp * 2;
+size_t basis_smem_bytes(int Lp, int nwb) {
+    return (size_t)Lp * 8 * 2 + (size_t)nwb * 2 * Lp * 8 + (size_t)nwb * 2 * Lp * 2;
 }
 
 }  // namespace
@@ -600,11 +608,9 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
 int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st) {
     const int Tt = (a.Pmax + 31) / 32;
     dim3 grid(Tt * (Tt + 1) / 2, a.nf);
-    k_gram<<<grid, 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_GRAM, st, k_gram<<<grid, 256, 0, st>>>(a));
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
-    k_chol_solve<<<a.nf, 256, xs_bytes, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_CHOL, st, k_chol_solve<<<a.nf, 256, xs_bytes, st>>>(a));
     return EAQHM_OK;
 }
 
@@ -616,7 +622,7 @@ extern "C" int64_t eaqhm_analysis_scratch_bytes(int32_t G, int32_t chunk, int32_
 extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const eaqhm_tracks* cur,
                               const eaqhm_knots* knots, double* best_am, int32_t adapt, int32_t nnz_max,
                               int32_t N_max, int32_t chunk, void* scratch, int64_t scratch_bytes,
-                              int32_t* status, void* stream) {
+                              int32_t* status, double* flop_stats, void* stream) {
     CHECK_ARG(tab && s && cur && knots && scratch && status);
     CHECK_ARG(adapt >= 0 && nnz_max > 0 && N_max > 0 && chunk > 0);
     CHECK_ARG(nnz_max <= 32767 && 2 * N_max + 1 <= 32767);
@@ -641,9 +647,13 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     A.R = (double2*)(base + l.off_R);
     A.x = (double2*)(base + l.off_x);
     A.status = status;
+    A.flop_stats = flop_stats;
     if (tab->nA == 0) return EAQHM_OK;
 
-    const size_t smem = basis_smem_bytes(l.Lp);
+    int nwb = kBasisWarps;
+    while (nwb > 1 && basis_smem_bytes(l.Lp, nwb) > 200 * 1024) nwb--;
+    A.nwb = nwb;
+    const size_t smem = basis_smem_bytes(l.Lp, nwb);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(k_basis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -655,24 +665,20 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     CUDA_TRY(cudaMemsetAsync(A.fb, 0, tab->G, st));
     if (adapt > 0) {
         A.j0 = 0; A.nf = tab->nA;
-        k_fallback_flags<<<(tab->nA * 32 + 255) / 256, 256, 0, st>>>(A);
-        CUDA_TRY(cudaGetLastError());
+        LAUNCH(KC_FALLBACK, st, k_fallback_flags<<<(tab->nA * 32 + 255) / 256, 256, 0, st>>>(A));
     }
     for (int j0 = 0; j0 < tab->nA; j0 += chunk) {
         A.j0 = j0;
         A.nf = min(chunk, tab->nA - j0);
-        k_active<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A);
-        CUDA_TRY(cudaGetLastError());
-        if (adapt == 0) k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A);
-        else k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A);
-        CUDA_TRY(cudaGetLastError());
+        LAUNCH(KC_ACTIVE, st, k_active<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
+        if (adapt == 0) LAUNCH(KC_BASIS, st, k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A));
+        else LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
         SolveArgs S;
         S.Ew = A.Ew; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
         S.nf = A.nf; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
         int rc = eaqhm_launch_gram_solve(S, st);
         if (rc != EAQHM_OK) return rc;
-        k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A);
-        CUDA_TRY(cudaGetLastError());
+        LAUNCH(KC_ACCEPT, st, k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
     }
     return EAQHM_OK;
 }
@@ -706,14 +712,14 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
         if (f0range) {
             CUDA_TRY(cudaMalloc(&d_f0, M * 8));
             CUDA_TRY(cudaMemcpy(d_f0, f0range, M * 8, cudaMemcpyHostToDevice));
-            k_basis_harmonic_explicit<<<1, 256>>>(d_s, d_f0, d_win, L, M, fs, d_Ew, Lp, Rb);
+            LAUNCH(KC_BASIS, 0, k_basis_harmonic_explicit<<<1, 256>>>(d_s, d_f0, d_win, L, M, fs, d_Ew, Lp, Rb));
         } else {
             CUDA_TRY(cudaMalloc(&d_am, (size_t)L * M * 8)); CUDA_TRY(cudaMalloc(&d_fm, (size_t)L * M * 8));
             CUDA_TRY(cudaMemcpy(d_am, am, (size_t)L * M * 8, cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMemcpy(d_fm, fm, (size_t)L * M * 8, cudaMemcpyHostToDevice));
-            k_basis_explicit<<<1, 256, (size_t)8 * Lp * 8>>>(d_s, d_am, d_fm, d_win, L, M, fs, d_Ew, Lp, Rb);
+            CHECK_ARG((size_t)8 * Lp * 8 <= 48 * 1024);
+            LAUNCH(KC_BASIS, 0, k_basis_explicit<<<1, 256, (size_t)8 * Lp * 8>>>(d_s, d_am, d_fm, d_win, L, M, fs, d_Ew, Lp, Rb));
         }
-        CUDA_TRY(cudaGetLastError());
         SolveArgs S;
         S.Ew = d_Ew; S.R = d_R; S.x = d_x; S.Mcols = d_meta; S.Lrows = d_meta + 1;
         S.nf = 1; S.Pmax = P; S.Pp = Pp; S.Lp = Lp; S.status = d_meta + 2;

@@ -35,6 +35,22 @@ void eaqhm_set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 
+// ---- launch accounting / per-kernel-class CUDA-event timing (capi.cu) -----------------------
+enum KernelClass {
+    KC_FALLBACK = 0, KC_ACTIVE, KC_BASIS, KC_GRAM, KC_CHOL, KC_ACCEPT, KC_RUN_MOMENTS, KC_A0_MOMENTS,
+    KC_INTERP, KC_SYNTH, KC_REDUCE, KC_VARPASS, KC_SNAPSHOT, KC_COUNT
+};
+void eaqhm_prof_begin(int kc, cudaStream_t st);
+void eaqhm_prof_end(int kc, cudaStream_t st);
+// LAUNCH(KC_X, stream, kernel<<<...>>>(...));  counts the launch and, when profiling is on, brackets it with events
+#define LAUNCH(kc, st, ...)                                                              \
+    do {                                                                                 \
+        eaqhm_prof_begin((kc), (st));                                                    \
+        __VA_ARGS__;                                                                     \
+        eaqhm_prof_end((kc), (st));                                                      \
+        CUDA_TRY(cudaGetLastError());                                                    \
+    } while (0)
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // ---- complex helpers on double2 (x = re, y = im) ---------------------------------------

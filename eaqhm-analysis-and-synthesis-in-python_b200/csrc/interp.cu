@@ -245,13 +245,10 @@ extern "C" int eaqhm_interpolate(const eaqhm_tables* tab, const eaqhm_knots* kno
     if (rc != EAQHM_OK) return rc;
     double* mom = (double*)work;
     const int nt = tab->Kmax * tab->U;
-    k_run_moments<<<(nt + 31) / 32, 32, 0, st>>>(*tab, *knots, mom);
-    CUDA_TRY(cudaGetLastError());
-    k_a0_moments<<<(tab->U + 31) / 32, 32, 0, st>>>(*tab, knots->a0, a0mom);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_RUN_MOMENTS, st, k_run_moments<<<(nt + 31) / 32, 32, 0, st>>>(*tab, *knots, mom));
+    LAUNCH(KC_A0_MOMENTS, st, k_a0_moments<<<(tab->U + 31) / 32, 32, 0, st>>>(*tab, knots->a0, a0mom));
     dim3 grid((tab->G + 127) / 128, tab->Kmax);
-    k_interp<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_INTERP, st, k_interp<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin));
     return EAQHM_OK;
 }
 
@@ -273,8 +270,7 @@ extern "C" int eaqhm_phase_integr_interpolation(const double* fm_recon, const do
         CUDA_TRY(cudaMemcpy(d_fm, fm_recon, length * 8, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d_ph, ph_recon, length * 8, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d_idx, indices, (size_t)n * 8, cudaMemcpyHostToDevice));
-        k_phase_integr_dense<<<(n - 1 + 127) / 128, 128>>>(d_fm, d_ph, d_idx, n, d_out);
-        CUDA_TRY(cudaGetLastError());
+        LAUNCH(KC_INTERP, 0, k_phase_integr_dense<<<(n - 1 + 127) / 128, 128>>>(d_fm, d_ph, d_idx, n, d_out));
         CUDA_TRY(cudaMemcpy(out, d_out, nout * 8, cudaMemcpyDeviceToHost));
         return EAQHM_OK;
     };

@@ -126,14 +126,10 @@ extern "C" int eaqhm_synthesize(const eaqhm_tables* tab, const eaqhm_tracks* tr,
     double* part = (double*)work;
     double* mean = part + (int64_t)tab->U * nblk;
     dim3 grid(nblk, tab->U);
-    k_synth<<<grid, kSynThreads, 0, st>>>(*tab, *tr, a0k, a0mom, det, s_hat, part, nblk);
-    CUDA_TRY(cudaGetLastError());
-    k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, mean, true);
-    CUDA_TRY(cudaGetLastError());
-    k_var_pass<<<grid, kSynThreads, 0, st>>>(*tab, det, s_hat, mean, part, nblk);
-    CUDA_TRY(cudaGetLastError());
-    k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, var_out, true);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_SYNTH, st, k_synth<<<grid, kSynThreads, 0, st>>>(*tab, *tr, a0k, a0mom, det, s_hat, part, nblk));
+    LAUNCH(KC_REDUCE, st, k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, mean, true));
+    LAUNCH(KC_VARPASS, st, k_var_pass<<<grid, kSynThreads, 0, st>>>(*tab, det, s_hat, mean, part, nblk));
+    LAUNCH(KC_REDUCE, st, k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, var_out, true));
     return EAQHM_OK;
 }
 
@@ -143,10 +139,8 @@ extern "C" int eaqhm_snapshot(const eaqhm_tables* tab, const uint8_t* improved, 
     CHECK_ARG(tab && improved && tr && knots && fm_fin && a0mom && s_hat && s_best && best);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 g1((tab->G + 127) / 128, tab->Kmax);
-    k_snapshot_knots<<<g1, 128, 0, st>>>(*tab, improved, *tr, fm_fin, knots->a0, a0mom, *best);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_SNAPSHOT, st, k_snapshot_knots<<<g1, 128, 0, st>>>(*tab, improved, *tr, fm_fin, knots->a0, a0mom, *best));
     dim3 g2(synth_nblk(tab->maxlen), tab->U);
-    k_snapshot_signal<<<g2, kSynThreads, 0, st>>>(*tab, improved, s_hat, s_best);
-    CUDA_TRY(cudaGetLastError());
+    LAUNCH(KC_SNAPSHOT, st, k_snapshot_signal<<<g2, kSynThreads, 0, st>>>(*tab, improved, s_hat, s_best));
     return EAQHM_OK;
 }

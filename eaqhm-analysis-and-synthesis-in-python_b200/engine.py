@@ -44,8 +44,13 @@ class Result:
     stats: dict = field(default_factory=dict)
 
 
+_h2d_counter = [0]
+
+
 def _dev(a, dtype, device):
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device, non_blocking=False)
+    a = np.ascontiguousarray(a, dtype=dtype)
+    _h2d_counter[0] += a.nbytes
+    return torch.from_numpy(a).to(device, non_blocking=False)
 
 
 class Engine:
@@ -57,6 +62,7 @@ class Engine:
             raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
         self.L = _lib.lib()
         self.device = torch.device(device)
+        _h2d_counter[0] = 0
         self.utts = list(utterances)
         U = len(self.utts)
         if U == 0:
@@ -110,6 +116,7 @@ class Engine:
         self.var = torch.zeros(U, **f64)
         self.improved = torch.zeros(U, dtype=torch.uint8, device=d)
         self.status = torch.zeros(2, dtype=torch.int32, device=d)
+        self.flops = torch.zeros(3, **f64)
         nA = int(self.t_alist.numel())
         if chunk is None:
             per_frame = self.L.eaqhm_analysis_scratch_bytes(0, 1, self.nnz_max, self.N_max)
@@ -129,7 +136,9 @@ class Engine:
         self.c_tr = _lib.Tracks(*[x.data_ptr() for x in self.tr])
         self.c_kn = _lib.Knots(*[x.data_ptr() for x in self.kn])
         self.c_best = _lib.Knots(*[x.data_ptr() for x in self.best])
-        self.launches = 0
+        self.h2d_bytes = _h2d_counter[0]
+        self.d2h_bytes = 0
+        self.useful_flops = dict(gram=0.0, chol=0.0, basis=0.0)
 
     # ------------------------------------------------------------------------------
     def _stream(self):
@@ -138,10 +147,12 @@ class Engine:
     def set_active(self, active):
         act = np.asarray(active, bool)
         self.t_active.copy_(torch.from_numpy(act.astype(np.uint8)))
+        self.h2d_bytes += self.U
         al = [self.alists[i] for i in range(self.U) if act[i]]
         al = np.concatenate(al) if al else np.zeros(0, np.int32)
         if len(al):
             self.t_alist[:len(al)].copy_(torch.from_numpy(al))
+            self.h2d_bytes += al.nbytes
         self.tab.nA = int(len(al))
         return int(len(al))
 
@@ -152,7 +163,7 @@ class Engine:
         _lib.check(self.L.eaqhm_analysis(C.byref(self.tab), self.s.data_ptr(), C.byref(self.c_tr), C.byref(self.c_kn),
                                          self.best[0].data_ptr(), a, self.nnz_max, self.N_max, self.chunk,
                                          self.scratch.data_ptr(), self.scratch.numel(), self.status.data_ptr(),
-                                         self._stream()))
+                                         self.flops.data_ptr(), self._stream()))
 
     def interpolate(self):
         """Stage B (functions.py:337-383)."""
@@ -176,19 +187,23 @@ class Engine:
                                          self._stream()))
 
     # ------------------------------------------------------------------------------
-    def run(self, on_adaptation=None):
-        """The adaptation loop (functions.py:163-402).  Returns one Result per utterance."""
+    def run_device(self, on_adaptation=None):
+        """The adaptation loop (functions.py:163-402) on the resident inputs; results stay on the device.
+        Returns (SRER per utterance, index of the best adaptation per utterance, frame solves)."""
         U = self.U
         active = np.ones(U, bool)
         SRER = [[] for _ in range(U)]
         best_a = np.zeros(U, int)
         frames_solved = 0
+        self.status.zero_()
+        self.flops.zero_()
         for a in range(self.maxAdpt + 1):
             nA = self.set_active(active)
             frames_solved += nA
             self.analysis(a)
             self.interpolate()
             var = self.synthesize().cpu().numpy()                           # the one host sync per adaptation
+            self.d2h_bytes += var.nbytes
             improved = np.zeros(U, bool)
             with np.errstate(all="ignore"):
                 for u in np.flatnonzero(active):
@@ -200,11 +215,18 @@ class Engine:
                         improved[u] = True
                         best_a[u] = a
             self.snapshot(improved)                                         # functions.py:397-402
+            self.h2d_bytes += U
             if on_adaptation is not None:
                 on_adaptation(a, SRER)
             if not active.any():
                 break
-        return self.results(SRER, best_a, frames_solved)
+        fl = self.flops.cpu().numpy()
+        self.useful_flops = dict(gram=float(fl[0]), chol=float(fl[1]), basis=float(fl[2]))
+        return SRER, best_a, frames_solved
+
+    def run(self, on_adaptation=None):
+        """Adaptation loop + copy of the results to host arrays.  Returns one Result per utterance."""
+        return self.results(*self.run_device(on_adaptation))
 
     def results(self, SRER, best_a, frames_solved=0):
         K, G = self.Kmax, self.G
@@ -212,6 +234,7 @@ class Engine:
         b_am, b_ph, b_fm = [x.view(K, G).cpu().numpy() for x in self.best[:3]]
         b_a0 = self.best[3].cpu().numpy()
         status = self.status.cpu().numpy()
+        self.d2h_bytes += s_best.nbytes + 3 * b_am.nbytes + b_a0.nbytes
         out = []
         for i, (u, f) in enumerate(zip(self.utts, self.ft)):
             g0, n = self.gfirst[i], f.No_ti

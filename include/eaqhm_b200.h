@@ -44,6 +44,16 @@ int         eaqhm_version(void);
 const char* eaqhm_last_error(void);
 int         eaqhm_device_count(void);
 
+/* Launch accounting and per-kernel-class device timing (CUDA events on the launching
+ * stream).  Counts are always kept; timing only while enabled.  eaqhm_profile_read
+ * synchronises the recorded events and returns accumulated milliseconds and launch
+ * counts for the eaqhm_profile_classes() kernel classes (names by index). */
+int         eaqhm_profile_enable(int on);
+int         eaqhm_profile_reset(void);
+int         eaqhm_profile_classes(void);
+const char* eaqhm_profile_name(int kernel_class);
+int         eaqhm_profile_read(double* ms, int64_t* counts, int32_t n);
+
 /* ---------------------------------------------------------------------------
  * Tables describing the frames of a batch (device pointers unless noted).
  * Mirrors the per-frame quantities of functions.py:148-157,176-194.
@@ -103,11 +113,14 @@ int64_t eaqhm_analysis_scratch_bytes(int32_t G, int32_t chunk, int32_t nnz_max, 
  * amplitude 10e-4 (the am_fin alias of functions.py:210,383,400).
  * `status` (device, int32[2]): [0] += frames whose matrix was not positive definite,
  * [1] += frames that used the fallback.
+ * `flop_stats` (device, double[3], may be NULL): += algorithmic flops of the frames
+ * analysed (Gram, Cholesky+solves, basis rhs) for the roofline report.
  * ------------------------------------------------------------------------- */
 int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const eaqhm_tracks* cur,
                    const eaqhm_knots* knots, double* best_am, int32_t adapt,
                    int32_t nnz_max, int32_t N_max, int32_t chunk,
-                   void* scratch, int64_t scratch_bytes, int32_t* status, void* stream);
+                   void* scratch, int64_t scratch_bytes, int32_t* status, double* flop_stats,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------
  * Stage B — interpolation between frame centres (functions.py:337-383): run

@@ -1,0 +1,281 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the golden fixtures made by
+the reference and against the oracle on seeded inputs.
+
+Tolerances (north_star): waveform 1e-7 absolute, SRER 0.01 dB, amplitudes / frequencies 1e-9 relative.
+"Relative" is taken per frame against the frame's largest amplitude for amplitudes, and per harmonic for
+the frequencies of harmonics within 60 dB of the frame maximum: weaker harmonics are below the
+conditioning noise of the reference's own normal-equation solve (cond(R) up to 1e6).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import eaqhm_oracle as O
+from common import GOLDEN, compare_to_golden, inputs_from_golden, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL_S = 1e-7
+TOL_SRER = 0.01
+TOL_REL = 1e-9
+
+
+def P(a):
+    from eaqhm_b200 import _lib
+    return np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(_lib.c_f64p)
+
+
+def utterance(inp):
+    from eaqhm_b200 import engine
+    return engine.Utterance(s=inp["s"], fs=inp["fs"], f0s=inp["f0s"], voiced5=inp["voiced5"],
+                            frame_step=inp["frame_step"], f0min=inp["f0min"], Kmax=inp["Kmax"], det_part=inp["det_part"])
+
+
+def run_cuda(inp, **kw):
+    from eaqhm_b200 import engine
+    eng = engine.Engine([utterance(inp)], step=inp["step"], maxAdpt=inp["maxAdpt"],
+                        analysisWindow=inp["analysisWindow"], **kw)
+    return eng.run()[0]
+
+
+def run_oracle(inp):
+    return O.eaqhm_oracle(inp["s"], inp["fs"], inp["f0s"], inp["voiced5"], inp["frame_step"], inp["f0min"],
+                          inp["Kmax"], step=inp["step"], maxAdpt=inp["maxAdpt"], analysisWindow=inp["analysisWindow"],
+                          det_part=inp["det_part"])
+
+
+def assert_close_results(res, ref):
+    assert len(res.SRER) == len(ref.SRER)
+    assert np.abs(np.array(res.SRER) - np.array(ref.SRER)).max() <= TOL_SRER
+    assert np.abs(res.s_recon - ref.s_recon).max() <= TOL_S
+    v = ref.isVoiced
+    assert (res.isVoiced == v).all() and (res.isSpeech == ref.isSpeech).all() and (res.ti == ref.ti).all()
+    assert ((res.am != 0) == (ref.am != 0)).all()
+    fmax = np.abs(ref.am[v]).max(axis=1, keepdims=True)
+    assert (np.abs(res.am[v] - ref.am[v]) / fmax).max() <= TOL_REL
+    strong = ref.am[v] > 1e-3 * fmax
+    assert (np.abs(res.fm[v] - ref.fm[v])[strong] / np.abs(ref.fm[v][strong])).max() <= TOL_REL
+    assert np.abs(res.a0 - ref.a0).max() <= TOL_REL
+
+
+# ---------------------------------------------------------------------------------------------
+# helper seams (functions.py:420,472,537) through the host-buffer C entry points
+# ---------------------------------------------------------------------------------------------
+def call_iqhm(lib, s, f0range, win, fs):
+    M = len(f0range)
+    amp, slope = np.zeros(2 * M), np.zeros(2 * M)
+    rc = lib.eaqhm_iqhmLS_complexamps(P(s), len(s), P(f0range), M, P(win), float(fs), P(amp), P(slope))
+    return rc, amp.view(complex), slope.view(complex)
+
+
+def call_eaqhm(lib, s, am, fm, win, fs):
+    M = am.shape[1]
+    amp, slope = np.zeros(2 * M), np.zeros(2 * M)
+    # P() keeps the temporaries alive only for the call; pass contiguous copies explicitly
+    am_c, fm_c = np.ascontiguousarray(am, float), np.ascontiguousarray(fm, float)
+    rc = lib.eaqhm_eaqhmLS_complexamps(P(s), len(s), am_c.ctypes.data_as(C.POINTER(C.c_double)),
+                                       fm_c.ctypes.data_as(C.POINTER(C.c_double)), M, P(win), float(fs),
+                                       amp.ctypes.data_as(C.POINTER(C.c_double)),
+                                       slope.ctypes.data_as(C.POINTER(C.c_double)))
+    return rc, amp.view(complex), slope.view(complex)
+
+
+def test_seams_match_reference_golden(lib):
+    h = np.load(GOLDEN + "/helpers.npz")
+    rc, a, b = call_iqhm(lib, h["iq_s"], h["iq_f0range"], h["iq_win"], 16000)
+    assert rc == 0
+    assert np.abs(a - h["iq_amp"]).max() <= TOL_REL * np.abs(h["iq_amp"]).max()
+    assert np.abs(b - h["iq_slope"]).max() <= TOL_REL * np.abs(h["iq_slope"]).max()
+    rc, a, b = call_eaqhm(lib, h["ea_s"], h["ea_am"], h["ea_fm"], h["ea_win"], 16000)
+    assert rc == 0
+    assert np.abs(a - h["ea_amp"]).max() <= TOL_REL * np.abs(h["ea_amp"]).max()
+    assert np.abs(b - h["ea_slope"]).max() <= TOL_REL * np.abs(h["ea_slope"]).max()
+    from eaqhm_b200 import _lib
+    idx = np.ascontiguousarray(h["pi_idx"], np.int64)
+    out = np.zeros(idx[-1] - idx[0] + 1)
+    rc = lib.eaqhm_phase_integr_interpolation(P(h["pi_fm"]), P(h["pi_ph"]), len(h["pi_fm"]),
+                                              idx.ctypes.data_as(_lib.c_i64p), len(idx), P(out))
+    assert rc == 0 and np.abs(out - h["pi_out"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("K,N,seed", [(1, 120, 0), (7, 120, 1), (31, 133, 2), (60, 150, 3), (86, 267, 4)])
+def test_iqhm_seam_recovers_known_stationary_harmonics(lib, K, N, seed):
+    """Known-answer test: a stationary harmonic signal is recovered at adaptation 0."""
+    rng = np.random.default_rng(seed)
+    fs, f0 = 16000, 7800.0 / (K + 0.5)
+    n = np.arange(-N, N + 1)
+    ck = (rng.uniform(0.1, 1, K) / np.arange(1, K + 1)) * np.exp(1j * rng.uniform(-np.pi, np.pi, K))
+    s = 0.05 + sum(2 * (ck[k] * np.exp(2j * np.pi * (k + 1) * f0 * n / fs)).real for k in range(K))
+    f0range = np.arange(-K, K + 1) * f0
+    win = np.blackman(2 * N + 1)
+    rc, a, b = call_iqhm(lib, s, f0range, win, fs)
+    assert rc == 0
+    assert abs(a[K] - 0.05) <= 1e-10
+    assert np.abs(a[K + 1:] - ck).max() <= 1e-10 and np.abs(a[:K][::-1] - ck.conj()).max() <= 1e-10
+    ao, bo = O.iqhmLS_complexamps(s, f0range, win, fs)
+    assert np.abs(a - ao).max() <= TOL_REL * np.abs(ao).max()
+
+
+@pytest.mark.parametrize("Kp,N,seed", [(1, 120, 0), (12, 127, 1), (40, 150, 2)])
+def test_eaqhm_seam_matches_oracle_on_chirps(lib, Kp, N, seed):
+    rng = np.random.default_rng(seed)
+    fs, f0 = 16000, 7000.0 / (Kp + 1)
+    n = np.arange(-N, N + 1)
+    fm = np.stack([(k + 1) * (f0 + 0.03 * n + 1e-4 * n ** 2) for k in range(Kp)], axis=1)
+    am = np.stack([(1.0 / (k + 1)) * (1 + 0.002 * n * np.cos(k + seed)) for k in range(Kp)], axis=1)
+    ph = 2 * np.pi * np.cumsum(fm, axis=0) / fs
+    s = (2 * am * np.cos(ph - ph[N] + rng.uniform(-3, 3, Kp)[None, :])).sum(axis=1) + 1e-3 * rng.standard_normal(len(n))
+    z = np.zeros((len(n), 1))
+    fm_all = np.concatenate((-fm[::-1], z, fm), axis=1)         # functions.py:284-285 (time-reversed mirror, Q2)
+    am_all = np.concatenate((am[::-1], z, am), axis=1)
+    win = np.hamming(len(n))
+    rc, a, b = call_eaqhm(lib, s, am_all, fm_all, win, fs)
+    assert rc == 0
+    ao, bo = O.eaqhmLS_complexamps(s, am_all, fm_all, win, fs)
+    assert np.abs(a - ao).max() <= TOL_REL * np.abs(ao).max()
+    assert np.abs(b - bo).max() <= 1e-8 * np.abs(bo).max()
+
+
+def test_seam_reports_singular_system(lib):
+    """Two identical columns: the reference's inv() raises LinAlgError; the C ABI returns EAQHM_E_NOTPD."""
+    N = 120
+    n = np.arange(-N, N + 1)
+    fm = np.stack([200.0 + 0 * n, 200.0 + 0 * n, 0.0 * n], axis=1)
+    am = np.ones_like(fm)
+    rc, a, b = call_eaqhm(lib, np.cos(0.1 * n), am, fm, np.hamming(len(n)), 16000)
+    assert rc == -3
+
+
+def test_phase_seam_random_segments(lib):
+    from eaqhm_b200 import _lib
+    rng = np.random.default_rng(3)
+    length = 2000
+    idx = np.concatenate(([30], 30 + np.cumsum(rng.integers(3, 40, 60)))).astype(np.int64)
+    fm = 2 * np.pi / 16000 * (3000 + 2500 * np.sin(np.arange(length) / 17.0))
+    ph = np.zeros(length)
+    ph[idx] = rng.uniform(-np.pi, np.pi, len(idx))
+    out = np.zeros(idx[-1] - idx[0] + 1)
+    rc = lib.eaqhm_phase_integr_interpolation(P(fm), P(ph), length, idx.ctypes.data_as(_lib.c_i64p), len(idx), P(out))
+    assert rc == 0
+    assert np.abs(out - O.phase_integr_interpolation(fm, ph, idx)).max() <= 1e-11
+
+
+# ---------------------------------------------------------------------------------------------
+# whole path against the reference's golden outputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["synth_a_adpt0", "synth_a_adpt1", "synth_a_adpt2", "synth_a_adpt3", "synth_low",
+                                  "synth_child_vo", "synth_48k", "sa19"])
+def test_cuda_path_matches_reference_golden(name):
+    g, kw = load_golden(name)
+    res = run_cuda(inputs_from_golden(g, kw))
+    c = compare_to_golden(res, g)
+    assert c["n_adapt"][0] == c["n_adapt"][1], c
+    assert c["flags_ok"] and c["support_equal"], c
+    assert c["dSRER"] <= TOL_SRER, c
+    assert c["ds"] <= TOL_S, c
+    assert c["am_rel_framemax"] <= TOL_REL, c
+    assert c["fm_rel_strong"] <= TOL_REL, c
+    assert c["a0_abs"] <= TOL_REL, c
+    assert res.stats["not_pd_frames"] == 0
+
+
+def test_sa19_srer_matches_published_values():
+    """The reference's only published vector (img/SA19out.JPG, README.md:46-48)."""
+    published = [17.86520945273994, 24.431728752204954, 24.67698055430504, 25.291120491477024, 25.497403658214047,
+                 25.446628776435006]
+    g, kw = load_golden("sa19")
+    res = run_cuda(inputs_from_golden(g, kw))
+    assert len(res.SRER) == 6 and res.n_adapt_best == 4
+    assert np.abs(np.array(res.SRER) - np.array(published)).max() <= 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA path against the oracle on fresh seeded inputs
+# ---------------------------------------------------------------------------------------------
+def synth_inputs(cfg, maxAdpt, voiced_only=False):
+    from eaqhm_b200 import host, synthetic
+    s, f0s = synthetic.make(cfg)
+    fs = cfg["fs"]
+    fstep = int(round(0.005 * fs))
+    n5 = len(np.arange(1, len(s), fstep))
+    Kmax = host.harmonic_capacity(fs, f0s)[1]
+    if voiced_only:
+        t5 = (np.arange(1, len(s), fstep) - 1) / fs
+        voiced5 = np.asarray(cfg["voiced_mask_of_t"](t5), bool)
+        det = host.voiced_only_target(s, voiced5, voiced5, fstep)
+    else:
+        voiced5, det = np.ones(n5, bool), None
+    return dict(s=s, fs=fs, f0s=f0s, voiced5=voiced5, frame_step=fstep, f0min=float(cfg["gender"][0]), Kmax=Kmax,
+                det_part=det, step=15, maxAdpt=maxAdpt, analysisWindow=32)
+
+
+@pytest.mark.parametrize("case", ["c2", "c3", "c5"])
+def test_cuda_path_matches_oracle_on_seeded_inputs(case):
+    from eaqhm_b200 import synthetic
+    if case == "c2":
+        cfg, vo = synthetic.config_c2(duration=0.35), False
+    elif case == "c3":
+        cfg, vo = synthetic.config_c3(123, duration=0.4), False
+    else:
+        cfg, vo = synthetic.config_c5(5, duration=0.9), True
+    inp = synth_inputs(cfg, maxAdpt=2, voiced_only=vo)
+    assert_close_results(run_cuda(inp), run_oracle(inp))
+
+
+def test_batch_equals_single_runs_bitwise():
+    """Utterance batching (config c3) must not change any utterance's result."""
+    from eaqhm_b200 import engine, synthetic
+    inps = [synth_inputs(synthetic.config_c3(i, duration=d), maxAdpt=3) for i, d in ((0, 0.3), (1, 0.45), (2, 0.25))]
+    singles = [run_cuda(i) for i in inps]
+    batch = engine.Engine([utterance(i) for i in inps], maxAdpt=3).run()
+    for a, b in zip(singles, batch):
+        assert a.SRER == b.SRER
+        assert (a.s_recon == b.s_recon).all() and (a.am == b.am[:, :a.am.shape[1]]).all()
+        assert (a.fm == b.fm[:, :a.fm.shape[1]]).all() and (a.ph == b.ph[:, :a.ph.shape[1]]).all()
+
+
+def test_chunked_analysis_equals_unchunked_bitwise():
+    from eaqhm_b200 import synthetic
+    inp = synth_inputs(synthetic.config_c3(9, duration=0.3), maxAdpt=2)
+    a, b = run_cuda(inp), run_cuda(inp, chunk=37)
+    assert a.SRER == b.SRER and (a.s_recon == b.s_recon).all() and (a.am == b.am).all()
+
+
+def test_rerun_is_deterministic():
+    from eaqhm_b200 import synthetic
+    inp = synth_inputs(synthetic.config_c3(4, duration=0.3), maxAdpt=2)
+    a, b = run_cuda(inp), run_cuda(inp)
+    assert a.SRER == b.SRER and (a.s_recon == b.s_recon).all() and (a.fm == b.fm).all()
+
+
+def test_properties_at_benchmark_shard_size():
+    """Size-independent properties on a multi-second c2 shard the oracle cannot finish quickly: SRER rises until
+    the stop, the returned waveform is the best adaptation's, every accepted frequency is positive and below Nyquist,
+    amplitude support equals frequency support."""
+    from eaqhm_b200 import synthetic
+    inp = synth_inputs(synthetic.config_c2(duration=4.0), maxAdpt=10)
+    res = run_cuda(inp)
+    sr = np.array(res.SRER)
+    assert (np.diff(sr[:-1]) > 0).all() or len(sr) <= 2
+    assert res.n_adapt_best == (len(sr) - 2 if sr[-1] <= sr[-2] else len(sr) - 1)
+    det = inp["s"]
+    srer_from_signal = 20 * np.log10(np.std(det) / np.std(det - res.s_recon))
+    assert abs(srer_from_signal - sr[res.n_adapt_best]) <= 1e-9
+    v = res.isVoiced
+    assert ((res.am[v] != 0) == (res.fm[v] != 0)).all()
+    assert (res.fm[v][res.am[v] != 0] > 0).all() and (res.fm[v] < 8000).all()
+    assert sr[res.n_adapt_best] > 15.0
+
+
+def test_fallback_path_matches_oracle():
+    """Quirks Q6/Q10: noise-only stretches in full-waveform mode lose every harmonic after a few adaptations; those
+    frames analyse the 140 Hz / 10e-4 fallback component (functions.py:204-242)."""
+    from eaqhm_b200 import synthetic
+    cfg = dict(fs=16000, duration=0.7, seed=77, gender=(250, 500),
+               f0_of_t=lambda t: 330.0 + 30 * np.sin(2 * np.pi * 2 * t),
+               voiced_mask_of_t=lambda t: np.mod(t, 0.35) < 0.2)
+    inp = synth_inputs(cfg, maxAdpt=4)
+    res, ref = run_cuda(inp), run_oracle(inp)
+    assert res.stats["fallback_frames"] > 0
+    assert_close_results(res, ref)

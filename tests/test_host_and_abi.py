@@ -1,0 +1,128 @@
+"""CPU: host-side logic (functions.py:95-161,176-194 restated in eaqhm_b200/host.py) and the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import ROOT, inputs_from_golden, load_golden
+from eaqhm_b200 import _lib, api, host
+
+
+def test_gender_limits():
+    assert host.gender_limits("male") == (70, 180)
+    assert host.gender_limits("female") == (160, 300)
+    assert host.gender_limits("child") == (300, 600)
+    assert host.gender_limits("other") == (70, 500)
+    assert host.gender_limits((90, 250)) == (90, 250)
+
+
+@pytest.mark.parametrize("name", ["sa19", "synth_a_adpt0", "synth_child_vo"])
+def test_mode_handling_matches_reference_flags(name):
+    g, kw = load_golden(name)
+    inp = inputs_from_golden(g, kw)
+    # the reference mutates its Frame list in place; the fixture holds the flags after the run
+    assert (np.asarray(inp["voiced5"]) == g["voiced5_final"]).all()
+    assert (np.asarray(inp["speech5"]) == g["speech5_final"]).all()
+    assert host.harmonic_capacity(inp["fs"], inp["f0s"])[1] == int(g["Kmax"])
+
+
+@pytest.mark.parametrize("name", ["sa19", "synth_child_vo"])
+def test_frame_tables_match_reference_flags(name):
+    g, kw = load_golden(name)
+    inp = inputs_from_golden(g, kw)
+    ft = host.FrameTables(len(inp["s"]), inp["fs"], inp["f0s"], inp["voiced5"], inp["frame_step"], inp["Kmax"],
+                          inp["step"], 3, inp["analysisWindow"])
+    sel = g["frame_sel"]
+    assert (ft.ti0[sel] == g["det_ti"]).all()
+    assert (ft.isSpeech[sel] == g["det_isSpeech"]).all()
+    assert (ft.analysed[sel] == g["det_isVoiced"]).all()
+    a = ft.analysed
+    assert (ft.N[a] >= 120).all() and (ft.K0[a] >= 1).all() and (ft.K0[a] <= inp["Kmax"]).all()
+    assert (ft.N[~a] == 0).all()
+    assert ft.own.sum() == len(inp["s"])
+    assert ft.f0stale == ft.f0[np.flatnonzero(a)[-1]]
+
+
+def test_window_half_length_rounds_half_to_even():
+    # functions.py:191 uses Python round(): (5/2)*(16000/128) = 312.5 -> 312 (half-up would give 313)
+    fs = 16000
+    f0s = np.array([[0.0, 128.0, 1.0]] * 400)
+    ft = host.FrameTables(20000, fs, f0s, np.ones(400, bool), 80, 60, pitchPeriods=5)
+    assert set(int(x) for x in ft.N[ft.analysed]) == {312}
+    ft = host.FrameTables(20000, fs, f0s, np.ones(400, bool), 80, 60, pitchPeriods=3)
+    assert set(int(x) for x in ft.N[ft.analysed]) == {188}      # 187.5 -> 188
+
+
+def test_window_past_signal_end_raises_like_reference():
+    fs = 48000
+    f0s = np.array([[0.0, 80.0, 1.0]] * 100)
+    with pytest.raises(IndexError):
+        host.FrameTables(6000, fs, f0s, np.ones(100, bool), 240, 300)   # N = 900 > analysisWindow*step
+
+
+def test_voiced_only_target_keeps_voiced_regions_only():
+    s = np.arange(1000, dtype=float)
+    speech = np.zeros(13, bool)
+    voiced = np.zeros(13, bool)
+    speech[3:6] = voiced[3:6] = True
+    ss = host.voiced_only_target(s, speech, voiced, 80)
+    ti = np.arange(1, 1000, 80)
+    lo, hi = ti[3] - 80, ti[5] + 80 + 1
+    assert (ss[lo:hi] == s[lo:hi]).all() and ss[:lo].sum() == 0 and ss[hi:].sum() == 0
+    speech[10:] = voiced[10:] = True        # region reaching the last frame is never copied (Q9)
+    assert (host.voiced_only_target(s, speech, voiced, 80) == ss).all()
+
+
+def test_pack_det_components_shapes_follow_reference_quirk_q8():
+    from eaqhm_b200.engine import Result
+    am = np.array([[0.0, 0.5, 0.0, 0.25, 0.0], [0, 0, 0, 0, 0.0]])
+    res = Result(s_recon=np.zeros(4), SRER=[1.0], ti=np.array([0, 15]), isSpeech=np.array([True, True]),
+                 isVoiced=np.array([True, False]), a0=np.array([0.1, 0.0]), am=am, fm=am * 1000, ph=am)
+    det = api.pack_det_components(res)
+    assert det[0].ak == [] and det[0].amplitudes.dtype == object and len(det[0].amplitudes) == 4
+    assert isinstance(det[0].amplitudes[0], int) and det[0].amplitudes[1].shape == (1,)
+    assert float(det[0].frange[3][0]) == 250.0 and det[1].a0 == [] and det[1].isVoiced is False
+    res.isVoiced[1] = True
+    with pytest.raises(IndexError):          # voiced frame without an accepted harmonic (misc.py:61-62)
+        api.pack_det_components(res)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    _lib.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "eaqhm_b200.h")).read()
+    declared = set(re.findall(r"\b(eaqhm_[A-Za-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.exported_symbols())
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().eaqhm_version() >= 100
+    assert _lib.lib().eaqhm_analysis_scratch_bytes(100, 10, 40, 150) > 0
+    assert _lib.lib().eaqhm_analysis_scratch_bytes(100, 0, 40, 150) < 0
+
+
+def test_struct_layout_matches_header():
+    # field order/sizes of the ctypes mirrors must follow include/eaqhm_b200.h
+    assert ctypes.sizeof(_lib.Tracks) == 24 and ctypes.sizeof(_lib.Knots) == 32
+    assert _lib.Tables.T.offset == 0 and _lib.Tables.maxlen.offset == 8 and _lib.Tables.G.offset == 16
+    assert _lib.Tables.fs.offset == 32 and _lib.Tables.pos.offset == 40 and _lib.Tables.nA.offset == 40 + 14 * 8
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from eaqhm_b200 import engine
+    g, kw = load_golden("synth_a_adpt0")
+    inp = inputs_from_golden(g, kw)
+    u = engine.Utterance(s=inp["s"], fs=inp["fs"], f0s=inp["f0s"], voiced5=inp["voiced5"],
+                         frame_step=inp["frame_step"], f0min=inp["f0min"], Kmax=inp["Kmax"])
+    with pytest.raises(_lib.EaqhmError):
+        engine.Engine([u])
+    amp = np.zeros(6)
+    rc = _lib.lib().eaqhm_iqhmLS_complexamps(
+        np.zeros(5).ctypes.data_as(_lib.c_f64p), 5, np.zeros(3).ctypes.data_as(_lib.c_f64p), 3,
+        np.ones(5).ctypes.data_as(_lib.c_f64p), 16000.0, amp.ctypes.data_as(_lib.c_f64p),
+        amp.ctypes.data_as(_lib.c_f64p))
+    assert rc == -4    # EAQHM_E_NODEVICE: no CPU fallback
