@@ -187,6 +187,7 @@ class OracleResult:
     window_lengths: np.ndarray          # (No_ti,) half window N per frame
     n_adapt_best: int = 0               # index of the adaptation whose outputs are returned
     per_adapt: list = field(default_factory=list)   # optional per-adaptation centre params
+    n_fallback: int = 0                 # frames that took the 140 Hz fallback (functions.py:204-242)
 
 
 def frame_gate(length, step, analysisWindow, voiced5, frame_step):
@@ -227,6 +228,7 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
     best = None
     per_adapt = []
     frames_idx = np.flatnonzero(analysed)
+    n_fallback = 0
 
     for a in range(maxAdpt + 1):
         a0_recon = np.zeros(length)
@@ -250,6 +252,7 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
                 window = np.hamming(2 * N + 1)                                      # :200
                 act = np.flatnonzero(fm_current[c])                                 # :202
                 if len(act) == 0:                                                   # :204-242 fallback (Q6)
+                    n_fallback += 1
                     fm_current[c, 0] = FALLBACK_FM
                     am_current[c, 0] = FALLBACK_AM
                     act = np.array([0])
@@ -336,4 +339,5 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
     return OracleResult(s_recon=s_recon, SRER=SRER, ti=c_all, isSpeech=speech.copy(),
                         isVoiced=analysed.copy(), a0=a0_fin[c_all].copy(), am=am_fin[c_all].copy(),
                         fm=fm_fin[c_all].copy(), ph=pm_fin[c_all].copy(),
-                        window_lengths=window_lengths, n_adapt_best=a_best, per_adapt=per_adapt)
+                        window_lengths=window_lengths, n_adapt_best=a_best, per_adapt=per_adapt,
+                        n_fallback=n_fallback)

@@ -54,7 +54,9 @@ def compare_to_golden(res, g, label=""):
     out["am_rel_framemax"] = float((np.abs(am_r - am_g) / fmax).max())
     strong = am_g > fmax * 1e-3                       # harmonics within 60 dB of the frame maximum
     fm_r, fm_g = res.fm[sel][v], g["det_fm"][v]
-    out["fm_rel_strong"] = float((np.abs(fm_r - fm_g)[strong] / np.abs(fm_g[strong])).max())
+    fsel = strong & (fm_g != 0)                      # fm is 0 where only the fallback amplitude was written (Q10)
+    out["fm_rel_strong"] = float((np.abs(fm_r - fm_g)[fsel] / np.abs(fm_g[fsel])).max())
+    out["fm_zero_equal"] = bool(((fm_r == 0) == (fm_g == 0)).all())
     out["am_rel_strong"] = float((np.abs(am_r - am_g)[strong] / np.abs(am_g[strong])).max())
     out["ph_abs_strong"] = float(np.abs(res.ph[sel][v] - g["det_ph"][v])[strong].max())
     out["a0_abs"] = float(np.abs(res.a0[sel] - g["det_a0"])[v].max())

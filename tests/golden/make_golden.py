@@ -143,6 +143,22 @@ def case_synth_48k():
     make_case("synth_48k", pcm, 48000, (70, 100), f0s, maxAdpt=1, analysisWindow=64)
 
 
+def silence_pcm():
+    """Harmonic signal with two stretches of digital silence: frames whose window is all zeros accept nothing at
+    adaptation 0 and take the 140 Hz fallback afterwards (functions.py:204-242, quirks Q6/Q10)."""
+    cfg = dict(fs=16000, duration=0.6, seed=21, f0_of_t=lambda t: 210 + 15 * np.sin(2 * np.pi * 2.5 * t))
+    pcm, f0s = synth_pcm(cfg)
+    pcm = pcm.copy()
+    pcm[2600:4100] = 0
+    pcm[6300:7000] = 0
+    return pcm, f0s
+
+
+def case_synth_silence():
+    pcm, f0s = silence_pcm()
+    make_case("synth_silence", pcm, 16000, (90, 250), f0s, maxAdpt=3)
+
+
 def case_sa19():
     fs, pcm = wavfile.read(os.path.join(ref_shim.REFERENCE_DIR, "SA19.WAV"))
     make_case("sa19", pcm, fs, "female", None, subsample=4)
@@ -193,7 +209,7 @@ CASES = {
     "synth_a0": lambda: case_synth_a(0), "synth_a1": lambda: case_synth_a(1),
     "synth_a2": lambda: case_synth_a(2), "synth_a3": lambda: case_synth_a(3),
     "synth_low": case_synth_low, "synth_child_vo": case_synth_child_voiced_only,
-    "synth_48k": case_synth_48k, "sa19": case_sa19,
+    "synth_48k": case_synth_48k, "synth_silence": case_synth_silence, "sa19": case_sa19,
 }
 
 if __name__ == "__main__":

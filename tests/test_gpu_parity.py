@@ -54,7 +54,8 @@ def assert_close_results(res, ref):
     assert ((res.am != 0) == (ref.am != 0)).all()
     fmax = np.abs(ref.am[v]).max(axis=1, keepdims=True)
     assert (np.abs(res.am[v] - ref.am[v]) / fmax).max() <= TOL_REL
-    strong = ref.am[v] > 1e-3 * fmax
+    strong = (ref.am[v] > 1e-3 * fmax) & (ref.fm[v] != 0)
+    assert ((res.fm[v] == 0) == (ref.fm[v] == 0)).all()
     assert (np.abs(res.fm[v] - ref.fm[v])[strong] / np.abs(ref.fm[v][strong])).max() <= TOL_REL
     assert np.abs(res.a0 - ref.a0).max() <= TOL_REL
 
@@ -138,13 +139,16 @@ def test_eaqhm_seam_matches_oracle_on_chirps(lib, Kp, N, seed):
 
 
 def test_seam_reports_singular_system(lib):
-    """Two identical columns: the reference's inv() raises LinAlgError; the C ABI returns EAQHM_E_NOTPD."""
+    """An all-zero window makes R exactly singular: the reference's inv() raises LinAlgError
+    (functions.py:530); the C ABI returns EAQHM_E_NOTPD."""
     N = 120
     n = np.arange(-N, N + 1)
-    fm = np.stack([200.0 + 0 * n, 200.0 + 0 * n, 0.0 * n], axis=1)
+    fm = np.stack([-200.0 + 0 * n, 0.0 * n, 200.0 + 0 * n], axis=1)
     am = np.ones_like(fm)
-    rc, a, b = call_eaqhm(lib, np.cos(0.1 * n), am, fm, np.hamming(len(n)), 16000)
+    rc, a, b = call_eaqhm(lib, np.cos(0.1 * n), am, fm, np.zeros(len(n)), 16000)
     assert rc == -3
+    with pytest.raises(np.linalg.LinAlgError):
+        O.eaqhmLS_complexamps(np.cos(0.1 * n), am, fm, np.zeros(len(n)), 16000)
 
 
 def test_phase_seam_random_segments(lib):
@@ -165,7 +169,7 @@ def test_phase_seam_random_segments(lib):
 # whole path against the reference's golden outputs
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["synth_a_adpt0", "synth_a_adpt1", "synth_a_adpt2", "synth_a_adpt3", "synth_low",
-                                  "synth_child_vo", "synth_48k", "sa19"])
+                                  "synth_child_vo", "synth_48k", "synth_silence", "sa19"])
 def test_cuda_path_matches_reference_golden(name):
     g, kw = load_golden(name)
     res = run_cuda(inputs_from_golden(g, kw))
@@ -268,14 +272,15 @@ def test_properties_at_benchmark_shard_size():
     assert sr[res.n_adapt_best] > 15.0
 
 
-def test_fallback_path_matches_oracle():
-    """Quirks Q6/Q10: noise-only stretches in full-waveform mode lose every harmonic after a few adaptations; those
-    frames analyse the 140 Hz / 10e-4 fallback component (functions.py:204-242)."""
-    from eaqhm_b200 import synthetic
-    cfg = dict(fs=16000, duration=0.7, seed=77, gender=(250, 500),
-               f0_of_t=lambda t: 330.0 + 30 * np.sin(2 * np.pi * 2 * t),
-               voiced_mask_of_t=lambda t: np.mod(t, 0.35) < 0.2)
-    inp = synth_inputs(cfg, maxAdpt=4)
+def test_fallback_path_matches_reference_and_oracle():
+    """Quirks Q6/Q10: frames inside digital silence accept nothing at adaptation 0 and analyse the 140 Hz / 10e-4
+    fallback component afterwards (functions.py:204-242); the in-place amplitude write shows up in the returned
+    parameters of the best adaptation (the am_fin alias)."""
+    g, kw = load_golden("synth_silence")
+    inp = inputs_from_golden(g, kw)
     res, ref = run_cuda(inp), run_oracle(inp)
-    assert res.stats["fallback_frames"] > 0
+    assert ref.n_fallback > 0 and res.stats["fallback_frames"] == ref.n_fallback
     assert_close_results(res, ref)
+    sel, v = g["frame_sel"], g["det_isVoiced"]
+    assert ((res.am[sel][v][:, 0] == 10e-4) == (g["det_am"][v][:, 0] == 10e-4)).all()
+    assert (g["det_am"][v][:, 0] == 10e-4).sum() > 0

@@ -47,7 +47,7 @@ def test_notaknot_spline_matches_scipy():
     assert np.abs(interp1d(x, y, kind=3)(xq) - O.notaknot_cubic(x, y, xq)).max() <= 1e-11
 
 
-@pytest.mark.parametrize("name", ["synth_a_adpt0", "synth_a_adpt3", "synth_child_vo"])
+@pytest.mark.parametrize("name", ["synth_a_adpt0", "synth_a_adpt3", "synth_child_vo", "synth_silence"])
 def test_oracle_matches_reference_golden(name):
     g, kw = load_golden(name)
     res = run_oracle(inputs_from_golden(g, kw))
