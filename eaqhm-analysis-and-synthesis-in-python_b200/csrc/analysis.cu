@@ -18,13 +18,13 @@ struct AnaArgs {
     double* best_am;
     int32_t adapt;
     int32_t j0, nf;                 // chunk of the analysed list: [j0, j0+nf)
-    int32_t nnz_max, Mmax, Pmax, Pp, Lp;
+    int32_t nnz_max, Mxmax, Pmax, Pp, Lp;
     int32_t nwb;                    // warps of the basis kernel that own a column buffer (smem bound for long windows)
     uint8_t* fb;                    // [G] fallback flags of this adaptation
-    int32_t* Mcols;                 // [chunk] columns of E2 per frame (2*nnz+1)
+    int32_t* Mcols;                 // [chunk] generic columns of E2 per frame (2*nnz; the DC column is kept apart)
     int32_t* Lrows;                 // [chunk] window samples per frame
     int16_t* act;                   // [chunk][nnz_max] active harmonic indices
-    double2* Ew;                    // [chunk][Pmax][Lp]
+    double* X;                      // [chunk][2 planes][Mxmax][Lp]  windowed basis w*E2, real and imaginary planes
     double2* R;                     // [chunk][Pmax+1][Pp]   (row P = conj(rhs))
     double2* x;                     // [chunk][Pmax]
     int32_t* status;
@@ -82,7 +82,7 @@ __global__ void k_active(AnaArgs A) {
         if (count > A.nnz_max) count = A.nnz_max;   // cannot happen: active set only shrinks
     }
     if (lane == 0) {
-        A.Mcols[jl] = 2 * count + 1;
+        A.Mcols[jl] = 2 * count;
         A.Lrows[jl] = 2 * A.t.N[g] + 1;
         if (A.flop_stats) {   // structure-aware minimum work of this frame
             const double M = 2.0 * count + 1.0, L = 2.0 * A.t.N[g] + 1.0, P = 2.0 * M;
@@ -95,9 +95,41 @@ __global__ void k_active(AnaArgs A) {
 
 // ---------------------------------------------------------------------------------------
 // basis: one CTA per frame, one warp per harmonic column pair (+f, time-reversed -f), plus DC.
-// Column order of E2: [0,nnz) positive harmonics, [nnz,2nnz) their mirrored partners, 2nnz = DC.
-// Unknown order of the LS system: p in [0,M) amplitudes, [M,2M) slopes (functions.py:455,519).
+// Generic columns of E2 (stored windowed, X = w*E2, as real / imaginary planes [col][n]):
+//   [0,nnz) positive harmonics, [nnz,2nnz) their mirrored partners.  The DC column is E2 = 1, i.e.
+//   X = w (real); its Gram rows are plain weighted sums of the other columns and are written here.
+// Unknown order of the LS system (P = 2*Mx + 2):
+//   [0,Mx) amplitudes, [Mx,2Mx) slopes of the generic columns, 2Mx = DC amplitude, 2Mx+1 = DC slope.
+// Rows written here into the augmented matrix R~ = [[R, b],[b^H, .]]: 2Mx, 2Mx+1 (DC) and P (conj(b)).
 // ---------------------------------------------------------------------------------------
+struct ColSums {   // weighted sums of one column X over the window
+    double bar, bai, bsr, bsi;          // sum X*ws, sum n*X*ws                 (ws = w*s)     -> rhs
+    double d0r, d0i, d1r, d1i, d2r, d2i; // sum X*w, sum n*X*w, sum n^2*X*w                    -> DC rows
+    __device__ __forceinline__ void zero() { bar = bai = bsr = bsi = d0r = d0i = d1r = d1i = d2r = d2i = 0.0; }
+    __device__ __forceinline__ void add(double xr, double xi, double nc, double wn, double v) {
+        bar += xr * v; bai += xi * v;
+        const double nxr = nc * xr, nxi = nc * xi;
+        bsr += nxr * v; bsi += nxi * v;
+        d0r += xr * wn; d0i += xi * wn;
+        d1r += nxr * wn; d1i += nxi * wn;
+        d2r += nc * nxr * wn; d2i += nc * nxi * wn;
+    }
+    __device__ __forceinline__ void reduce() {
+        bar = warp_sum(bar); bai = warp_sum(bai); bsr = warp_sum(bsr); bsi = warp_sum(bsi);
+        d0r = warp_sum(d0r); d0i = warp_sum(d0i); d1r = warp_sum(d1r); d1i = warp_sum(d1i);
+        d2r = warp_sum(d2r); d2i = warp_sum(d2i);
+    }
+    // rows of R~: Rb = row P (conj rhs), Rd0 = row 2Mx, Rd1 = row 2Mx+1 (null without DC)
+    __device__ __forceinline__ void store(int col, int Mx, double2* Rb, double2* Rd0, double2* Rd1) const {
+        Rb[col] = make_double2(bar, bai);
+        Rb[Mx + col] = make_double2(bsr, bsi);
+        if (Rd0) {
+            Rd0[col] = make_double2(d0r, d0i);       Rd0[Mx + col] = make_double2(d1r, d1i);
+            Rd1[col] = make_double2(d1r, d1i);       Rd1[Mx + col] = make_double2(d2r, d2i);
+        }
+    }
+};
+
 template <bool ADAPT>
 __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -105,7 +137,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     const int jl = blockIdx.x;
     const int g = A.t.alist[A.j0 + jl];
     const int N = A.t.N[g], L = 2 * N + 1;
-    const int M = A.Mcols[jl], nz = (M - 1) / 2, P = 2 * M;
+    const int Mx = A.Mcols[jl], nz = Mx / 2, P = 2 * Mx + 2;
     const int u = A.t.utt[g];
     const int64_t us = A.t.ustart[u], ul = A.t.ulen[u];
     const int64_t cl = A.t.pos[g] - us;
@@ -132,33 +164,38 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     }
     __syncthreads();
 
-    double2* EwF = A.Ew + (size_t)jl * A.Pmax * A.Lp;
-    double2* Rb = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp + (size_t)P * A.Pp;   // row P: conj(rhs)
+    double* Xr = A.X + (size_t)jl * 2 * A.Mxmax * A.Lp;
+    double* Xi = Xr + (size_t)A.Mxmax * A.Lp;
+    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+    double2* Rb = RF + (size_t)P * A.Pp;
+    double2* Rd0 = RF + (size_t)(2 * Mx) * A.Pp;
+    double2* Rd1 = RF + (size_t)(2 * Mx + 1) * A.Pp;
     const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
     const double f0 = A.t.f0[g];
 
     for (int it = warp; it <= nz && warp < A.nwb; it += A.nwb) {
-        if (it == nz) {   // DC column: E2 = 1 (fm = 0, am = 0 -> (eps+0)/(0+eps) = 1)
-            double s0 = 0.0, s1 = 0.0;
-            double2* e0 = EwF + (size_t)(2 * nz) * A.Lp;
-            double2* e1 = EwF + (size_t)(M + 2 * nz) * A.Lp;
+        if (it == nz) {   // DC column: E2 = 1 (fm = 0, am = 0 -> (eps+0)/(0+eps) = 1), X = w
+            double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
             for (int n = lane; n < L; n += 32) {
-                const double wn = w[n], nc = (double)(n - N);
-                e0[n] = make_double2(wn, 0.0);
-                e1[n] = make_double2(nc * wn, 0.0);
-                s0 += wn * ws[n];
-                s1 += nc * wn * ws[n];
+                const double wn = w[n], nc = (double)(n - N), v = ws[n];
+                s0 += wn * v;        s1 += nc * wn * v;
+                q0 += wn * wn;       q1 += nc * wn * wn;      q2 += nc * nc * wn * wn;
             }
-            s0 = warp_sum(s0); s1 = warp_sum(s1);
-            if (lane == 0) { Rb[2 * nz] = make_double2(s0, 0.0); Rb[M + 2 * nz] = make_double2(s1, 0.0); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1); q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2);
+            if (lane == 0) {
+                Rb[2 * Mx] = make_double2(s0, 0.0);       Rb[2 * Mx + 1] = make_double2(s1, 0.0);
+                Rd0[2 * Mx] = make_double2(q0, 0.0);
+                Rd1[2 * Mx] = make_double2(q1, 0.0);      Rd1[2 * Mx + 1] = make_double2(q2, 0.0);
+            }
             continue;
         }
         const int k = act[it];
-        double2* ep0 = EwF + (size_t)it * A.Lp;
-        double2* ep1 = EwF + (size_t)(M + it) * A.Lp;
-        double2* en0 = EwF + (size_t)(nz + it) * A.Lp;
-        double2* en1 = EwF + (size_t)(M + nz + it) * A.Lp;
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double* pr = Xr + (size_t)it * A.Lp;
+        double* pi = Xi + (size_t)it * A.Lp;
+        double* nr = Xr + (size_t)(nz + it) * A.Lp;
+        double* ni = Xi + (size_t)(nz + it) * A.Lp;
+        ColSums cp, cn;
+        cp.zero(); cn.zero();
 
         if (!ADAPT) {
             // functions.py:453-455: t = (n*2*pi*f)/fs with f = (k+1)*f0; the -f column is the conjugate
@@ -169,11 +206,10 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 double sn, cs;
                 sincos(t, &sn, &cs);
                 const double wn = w[n], xr = cs * wn, xi = sn * wn, v = ws[n];
-                ep0[n] = make_double2(xr, xi);       ep1[n] = make_double2(nc * xr, nc * xi);
-                en0[n] = make_double2(xr, -xi);      en1[n] = make_double2(nc * xr, -(nc * xi));
-                acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+                pr[n] = xr; pi[n] = xi; nr[n] = xr; ni[n] = -xi;
+                cp.add(xr, xi, nc, wn, v);
+                cn.add(xr, -xi, nc, wn, v);
             }
-            acc[4] = acc[0]; acc[5] = -acc[1]; acc[6] = acc[2]; acc[7] = -acc[3];
         } else {
             // 1. gather the window of fm_current / am_current (functions.py:244-245); column 0 sees the
             //    in-place fallback writes of this and earlier frames (Q6, functions.py:209-210)
@@ -223,7 +259,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                         f = ((fmw[q] - fmw[p]) / dx) * xx + fmw[p];
                         a = ((amw[q] - amw[p]) / dx) * xx + amw[p];
                     }
-                    // neighbours are non-zero samples: never written here, and zero samples are read by no other lane
+                    // neighbours p, q are non-zero samples: never written here; zero samples are read by their own lane only
                     fmw[n] = f; amw[n] = a;
                 }
             }
@@ -254,8 +290,8 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                     sincos(t, &sn, &cs);
                     const double r = (kAmEps + amw[n]) / aden;
                     const double xr = (r * cs) * wn, xi = (r * sn) * wn;
-                    ep0[n] = make_double2(xr, xi);   ep1[n] = make_double2(nc * xr, nc * xi);
-                    acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+                    pr[n] = xr; pi[n] = xi;
+                    cp.add(xr, xi, nc, wn, v);
                 }
                 {
                     const int m2 = L - 2 - n;
@@ -264,28 +300,30 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                     sincos(t, &sn, &cs);
                     const double r = (kAmEps + amw[L - 1 - n]) / aden;
                     const double xr = (r * cs) * wn, xi = (r * sn) * wn;
-                    en0[n] = make_double2(xr, xi);   en1[n] = make_double2(nc * xr, nc * xi);
-                    acc[4] += xr * v; acc[5] += xi * v; acc[6] += nc * xr * v; acc[7] += nc * xi * v;
+                    nr[n] = xr; ni[n] = xi;
+                    cn.add(xr, xi, nc, wn, v);
                 }
             }
         }
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = warp_sum(acc[q]);
+        cp.reduce(); cn.reduce();
         if (lane == 0) {
-            Rb[it] = make_double2(acc[0], acc[1]);           Rb[M + it] = make_double2(acc[2], acc[3]);
-            Rb[nz + it] = make_double2(acc[4], acc[5]);      Rb[M + nz + it] = make_double2(acc[6], acc[7]);
+            cp.store(it, Mx, Rb, Rd0, Rd1);
+            cn.store(nz + it, Mx, Rb, Rd0, Rd1);
         }
         __syncwarp();
     }
 }
 
-// explicit-column basis for the eaqhmLS_complexamps seam (functions.py:472-519): am, fm [L][M] row-major
+// explicit-column basis for the eaqhmLS_complexamps seam (functions.py:472-519): am, fm [L][M] row-major;
+// every column (the DC one included) is a generic column, no separate DC rows (P = 2M)
 __global__ void k_basis_explicit(const double* s, const double* am, const double* fm, const double* win,
-                                 int L, int M, double fs, double2* Ew, int Lp, double2* Rb) {
+                                 int L, int M, double fs, double* X, int Lp, double2* Rb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* S = reinterpret_cast<double*>(smem_raw) + (size_t)(threadIdx.x >> 5) * Lp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int mid = (L - 1) / 2;
+    double* Xr = X;
+    double* Xi = X + (size_t)M * Lp;
     for (int c = warp; c < M; c += nw) {
         double run = 0.0;
         for (int base = 0; base < L; base += 32) {
@@ -302,92 +340,220 @@ __global__ void k_basis_explicit(const double* s, const double* am, const double
         }
         __syncwarp();
         const double Smid = S[mid], aden = am[(size_t)mid * M + c] + kAmEps;
-        double acc[4] = {0, 0, 0, 0};
+        ColSums cs_;
+        cs_.zero();
         for (int n = lane; n < L; n += 32) {
             const double nc = (double)(n - mid), wn = win[n], v = wn * s[n];
             double sn, cs;
             sincos((kTwoPi * (S[n] - Smid)) / fs, &sn, &cs);
             const double r = (kAmEps + am[(size_t)n * M + c]) / aden;
             const double xr = (r * cs) * wn, xi = (r * sn) * wn;
-            Ew[(size_t)c * Lp + n] = make_double2(xr, xi);
-            Ew[(size_t)(M + c) * Lp + n] = make_double2(nc * xr, nc * xi);
-            acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+            Xr[(size_t)c * Lp + n] = xr; Xi[(size_t)c * Lp + n] = xi;
+            cs_.add(xr, xi, nc, wn, v);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++) acc[q] = warp_sum(acc[q]);
-        if (lane == 0) { Rb[c] = make_double2(acc[0], acc[1]); Rb[M + c] = make_double2(acc[2], acc[3]); }
+        cs_.reduce();
+        if (lane == 0) cs_.store(c, M, Rb, nullptr, nullptr);
         __syncwarp();
     }
 }
 
 // explicit-frequency basis for the iqhmLS_complexamps seam (functions.py:420-464)
 __global__ void k_basis_harmonic_explicit(const double* s, const double* f0range, const double* win, int L, int M,
-                                          double fs, double2* Ew, int Lp, double2* Rb) {
+                                          double fs, double* X, int Lp, double2* Rb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double midlen = (double)(L - 1) / 2.0;
+    double* Xr = X;
+    double* Xi = X + (size_t)M * Lp;
     for (int c = warp; c < M; c += nw) {
         const double fk = f0range[c];
-        double acc[4] = {0, 0, 0, 0};
+        ColSums cs_;
+        cs_.zero();
         for (int n = lane; n < L; n += 32) {
             const double nc = (double)n - midlen, wn = win[n], v = wn * s[n];
             double sn, cs;
             sincos((((nc * 2.0) * kPi) * fk) / fs, &sn, &cs);
             const double xr = cs * wn, xi = sn * wn;
-            Ew[(size_t)c * Lp + n] = make_double2(xr, xi);
-            Ew[(size_t)(M + c) * Lp + n] = make_double2(nc * xr, nc * xi);
-            acc[0] += xr * v; acc[1] += xi * v; acc[2] += nc * xr * v; acc[3] += nc * xi * v;
+            Xr[(size_t)c * Lp + n] = xr; Xi[(size_t)c * Lp + n] = xi;
+            cs_.add(xr, xi, nc, wn, v);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++) acc[q] = warp_sum(acc[q]);
-        if (lane == 0) { Rb[c] = make_double2(acc[0], acc[1]); Rb[M + c] = make_double2(acc[2], acc[3]); }
+        cs_.reduce();
+        if (lane == 0) cs_.store(c, M, Rb, nullptr, nullptr);
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// Gram R = Ew^H Ew, lower triangle (functions.py:459,524).  v1: 32x32 complex tiles, DFMA.
+// Gram (functions.py:459,524): R = E_w^H E_w with E_w = [X, n*X] has the block form
+// [[A, B],[B^H, C]], A = X^H X, B = X^H (n X), C = X^H (n^2 X), all three Hermitian (the weights
+// w^2, n w^2, n^2 w^2 are real), so three Hermitian half-Grams of the Mx generic columns replace one of
+// 2Mx columns (12 L Mx^2 instead of 16 L Mx^2 real flops).
+//
+// FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA; shares the FP64 pipe with DFMA at the same peak but needs
+// 8x fewer issue slots and operand reads).  CTA = 4 warps = 32x32 complex outputs x 3 weights; each warp a
+// 16x16 tile as 2x2 DMMA sub-tiles; operands staged through shared memory by cp.async, double buffered,
+// [col][n] with pitch 36 doubles (conflict-free for the fragment pattern).  Complex product by real parts:
+// Gr = Xr^T Xr' + Xi^T Xi', Gi = Xr^T Xi' - Xi^T Xr'; the weights n, n^2 scale the B fragments in registers.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gram(SolveArgs A) {
+constexpr int kGT = 32;      // CTA tile edge (columns)
+constexpr int kGK = 32;      // samples per pipeline stage
+constexpr int kGP = 36;      // shared-memory pitch in doubles (== 4 mod 16)
+constexpr int kGramSmem = 2 /*stage*/ * 2 /*panel*/ * 2 /*plane*/ * kGT * kGP * 8;
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(128, 3) k_gram(SolveArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int jl = blockIdx.y;
-    const int P = 2 * A.Mcols[jl], L = A.Lrows[jl];
+    const int Mx = A.Mcols[jl], L = A.Lrows[jl], N = (L - 1) / 2;
     const int tp = blockIdx.x;
     int ti = (int)((sqrt(8.0 * tp + 1.0) - 1.0) * 0.5);
     while (ti * (ti + 1) / 2 > tp) ti--;
     while ((ti + 1) * (ti + 2) / 2 <= tp) ti++;
     const int tj = tp - ti * (ti + 1) / 2;
-    if (ti * 32 >= P) return;
-    __shared__ double2 As[32][33], Bs[32][33];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const double2* EwF = A.Ew + (size_t)jl * A.Pmax * A.Lp;
-    double2 acc[2][2];
+    if (ti * kGT >= Mx) return;
+    const bool diag = ti == tj;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = warp >> 1, wj = warp & 1;
+    const int lr = lane >> 2, lc = lane & 3;
+
+    // sm[stage][panel][plane][col][kGP]
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    auto sm_at = [&](int stage, int panel, int plane) {
+        return sm + ((size_t)((stage * 2 + panel) * 2 + plane)) * kGT * kGP;
+    };
+    const double* Xf = A.X + (size_t)jl * 2 * A.Mxmax * A.Lp;
+    const size_t plane_stride = (size_t)A.Mxmax * A.Lp;
+
+    auto load_stage = [&](int chunk, int stage) {
+        const int n0 = chunk * kGK;
+        // per panel and plane: 32 cols x 32 samples = 512 16-byte pieces; 128 threads x 4
+        const int npanel = diag ? 1 : 2;
+        for (int pnl = 0; pnl < npanel; pnl++) {
+            const int c0 = (pnl == 0 ? ti : tj) * kGT;
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+            for (int plane = 0; plane < 2; plane++) {
+                double* dst = sm_at(stage, pnl, plane);
 #pragma unroll
-        for (int j = 0; j < 2; j++) acc[i][j] = make_double2(0.0, 0.0);
-    for (int n0 = 0; n0 < L; n0 += 32) {
+                for (int e = 0; e < 4; e++) {
+                    const int idx = tid + e * 128;          // 0..511
+                    const int col = idx >> 4, pc = idx & 15; // piece pc covers samples n0 + 2pc, +1
+                    const int n = n0 + 2 * pc;
+                    const int gc = c0 + col;
+                    int bytes = 0;
+                    if (gc < Mx) bytes = (n + 1 < L) ? 16 : ((n < L) ? 8 : 0);
+                    const int gcs = gc < Mx ? gc : 0, ns = n < L ? n : 0;
+                    cp_async16(dst + col * kGP + 2 * pc, Xf + plane * plane_stride + (size_t)gcs * A.Lp + ns, bytes);
+                }
+            }
+        }
+    };
+
+    // sub-tile activity (warp uniform): rows/cols inside Mx, and on or below the diagonal at 8x8 granularity
+    const int i0 = ti * kGT + wi * 16, j0 = tj * kGT + wj * 16;
+    bool act_[2][2];
+    bool any = false;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int idx = tid + e * 256, r = idx >> 5, nn = idx & 31;
-            const int n = n0 + nn, pa = ti * 32 + r, pb = tj * 32 + r;
-            As[r][nn] = (pa < P && n < L) ? EwF[(size_t)pa * A.Lp + n] : make_double2(0.0, 0.0);
-            Bs[r][nn] = (pb < P && n < L) ? EwF[(size_t)pb * A.Lp + n] : make_double2(0.0, 0.0);
+    for (int si = 0; si < 2; si++)
+#pragma unroll
+        for (int sj = 0; sj < 2; sj++) {
+            act_[si][sj] = (i0 + si * 8 < Mx) && (j0 + sj * 8 < Mx) && (j0 + sj * 8 <= i0 + si * 8);
+            any |= act_[si][sj];
+        }
+
+    double acc[2][2][3][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int d = 0; d < 2; d++) acc[a][b][c][d][0] = acc[a][b][c][d][1] = 0.0;
+
+    const int nchunks = (L + kGK - 1) / kGK;
+    load_stage(0, 0);
+    cp_async_commit();
+    for (int c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) {
+            load_stage(c + 1, (c + 1) & 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
-#pragma unroll 8
-        for (int nn = 0; nn < 32; nn++) {
-            const double2 a0 = As[ty * 2][nn], a1 = As[ty * 2 + 1][nn];
-            const double2 b0 = Bs[tx * 2][nn], b1 = Bs[tx * 2 + 1][nn];
-            cfma_conj_a(acc[0][0], a0, b0); cfma_conj_a(acc[0][1], a0, b1);
-            cfma_conj_a(acc[1][0], a1, b0); cfma_conj_a(acc[1][1], a1, b1);
+        if (any) {
+            const int st = c & 1;
+            const double* ar_s = sm_at(st, 0, 0) + (wi * 16 + lr) * kGP + lc;
+            const double* ai_s = sm_at(st, 0, 1) + (wi * 16 + lr) * kGP + lc;
+            const double* br_s = sm_at(st, diag ? 0 : 1, 0) + (wj * 16 + lr) * kGP + lc;
+            const double* bi_s = sm_at(st, diag ? 0 : 1, 1) + (wj * 16 + lr) * kGP + lc;
+#pragma unroll
+            for (int kk = 0; kk < kGK; kk += 4) {
+                const double nc = (double)(c * kGK + kk + lc - N), nc2 = nc * nc;
+                double ar[2], ai[2], nai[2], br[2][3], bi[2][3];
+#pragma unroll
+                for (int si = 0; si < 2; si++) {
+                    ar[si] = ar_s[si * 8 * kGP + kk];
+                    ai[si] = ai_s[si * 8 * kGP + kk];
+                    nai[si] = -ai[si];
+                }
+#pragma unroll
+                for (int sj = 0; sj < 2; sj++) {
+                    const double r = br_s[sj * 8 * kGP + kk], i = bi_s[sj * 8 * kGP + kk];
+                    br[sj][0] = r; br[sj][1] = r * nc; br[sj][2] = r * nc2;
+                    bi[sj][0] = i; bi[sj][1] = i * nc; bi[sj][2] = i * nc2;
+                }
+#pragma unroll
+                for (int si = 0; si < 2; si++)
+#pragma unroll
+                    for (int sj = 0; sj < 2; sj++)
+                        if (act_[si][sj]) {
+#pragma unroll
+                            for (int wt = 0; wt < 3; wt++) {
+                                dmma884(acc[si][sj][wt][0], ar[si], br[sj][wt]);
+                                dmma884(acc[si][sj][wt][1], ar[si], bi[sj][wt]);
+                                dmma884(acc[si][sj][wt][0], ai[si], bi[sj][wt]);
+                                dmma884(acc[si][sj][wt][1], nai[si], br[sj][wt]);
+                            }
+                        }
+            }
         }
         __syncthreads();
     }
+
+    // epilogue: C fragment element (row lr, cols 2*lc, 2*lc+1) of each 8x8 sub-tile
     double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+    const int Pp = A.Pp;
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int si = 0; si < 2; si++)
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int p = ti * 32 + ty * 2 + i, q = tj * 32 + tx * 2 + j;
-            if (p < P && q <= p) RF[(size_t)p * A.Pp + q] = acc[i][j];
+        for (int sj = 0; sj < 2; sj++) {
+            if (!act_[si][sj]) continue;
+            const int i = i0 + si * 8 + lr;
+            const bool offdiag_sub = (j0 + sj * 8) < (i0 + si * 8);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = j0 + sj * 8 + 2 * lc + e;
+                if (i >= Mx || j >= Mx) continue;
+                const double2 a = make_double2(acc[si][sj][0][0][e], acc[si][sj][0][1][e]);
+                const double2 b = make_double2(acc[si][sj][1][0][e], acc[si][sj][1][1][e]);
+                const double2 cc = make_double2(acc[si][sj][2][0][e], acc[si][sj][2][1][e]);
+                if (j <= i) {
+                    RF[(size_t)i * Pp + j] = a;                       // A block
+                    RF[(size_t)(Mx + i) * Pp + Mx + j] = cc;          // C block
+                }
+                RF[(size_t)(Mx + i) * Pp + j] = b;                    // B^H block (= B, Hermitian), full
+                if (offdiag_sub) RF[(size_t)(Mx + j) * Pp + i] = make_double2(b.x, -b.y);
+            }
         }
 }
 
@@ -398,7 +564,7 @@ __global__ void __launch_bounds__(256) k_gram(SolveArgs A) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_chol_solve(SolveArgs A) {
     const int jl = blockIdx.x, tid = threadIdx.x;
-    const int P = 2 * A.Mcols[jl];
+    const int P = 2 * A.Mcols[jl] + 2 * A.dc;
     double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
     const int Pp = A.Pp;
     __shared__ double2 Bk[kNb][kNb + 1];     // L[jb+c][kb+k]
@@ -543,7 +709,7 @@ __global__ void k_accept(AnaArgs A) {
     const int jl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (jl >= A.nf) return;
     const int g = A.t.alist[A.j0 + jl];
-    const int M = A.Mcols[jl], nz = (M - 1) / 2;
+    const int M = A.Mcols[jl], nz = M / 2;      // M generic columns; solution: amps [0,M), slopes [M,2M), DC at 2M
     const int u = A.t.utt[g];
     const double2* x = A.x + (size_t)jl * A.Pmax;
     const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
@@ -555,7 +721,7 @@ __global__ void k_accept(AnaArgs A) {
     const double f0u = A.adapt == 0 ? A.t.f0[g] : A.t.f0stale[u];         // stale f0 for a >= 1 (Q1)
     const double h = f0u / (double)(A.adapt + 1);                          // functions.py:310
     const bool correct = f0u > A.t.f0min[u];                               // functions.py:321
-    if (lane == 0) A.k.a0[g] = x[2 * nz].x;                                // functions.py:303
+    if (lane == 0) A.k.a0[g] = x[2 * M].x;                                 // functions.py:303
     const int64_t c = A.t.pos[g];
     for (int it = lane; it < nz; it += 32) {
         const int k = act[it];
@@ -590,15 +756,15 @@ size_t basis_smem_bytes(int Lp, int nwb) {
 AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max) {
     AnaLayout l;
     l.nnz_max = nnz_max;
-    l.Mmax = 2 * nnz_max + 1;
-    l.Pmax = 2 * l.Mmax;
+    l.Mxmax = 2 * nnz_max;
+    l.Pmax = 2 * l.Mxmax + 2;
     l.Pp = (int32_t)align_up(l.Pmax, kNb);
     l.Lp = (int32_t)align_up(2 * N_max + 1, 4);
     int64_t o = 0;
     l.off_fb = o;  o = align_up(o + G, 256);
     l.off_M = o;   o = align_up(o + (int64_t)chunk * 4 * 2, 256);
     l.off_act = o; o = align_up(o + (int64_t)chunk * nnz_max * 2, 256);
-    l.off_Ew = o;  o = align_up(o + (int64_t)chunk * l.Pmax * l.Lp * 16, 256);
+    l.off_X = o;   o = align_up(o + (int64_t)chunk * 2 * l.Mxmax * l.Lp * 8, 256);
     l.off_R = o;   o = align_up(o + (int64_t)chunk * (l.Pmax + 1) * l.Pp * 16, 256);
     l.off_x = o;   o = align_up(o + (int64_t)chunk * l.Pmax * 16, 256);
     l.total = o;
@@ -606,9 +772,14 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
 }
 
 int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st) {
-    const int Tt = (a.Pmax + 31) / 32;
+    static bool gram_attr = false;
+    if (!gram_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
+        gram_attr = true;
+    }
+    const int Tt = (a.Mxmax + kGT - 1) / kGT;
     dim3 grid(Tt * (Tt + 1) / 2, a.nf);
-    LAUNCH(KC_GRAM, st, k_gram<<<grid, 256, 0, st>>>(a));
+    LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
     LAUNCH(KC_CHOL, st, k_chol_solve<<<a.nf, 256, xs_bytes, st>>>(a));
     return EAQHM_OK;
@@ -638,12 +809,12 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     A.k = *knots;
     A.best_am = best_am;
     A.adapt = adapt;
-    A.nnz_max = l.nnz_max; A.Mmax = l.Mmax; A.Pmax = l.Pmax; A.Pp = l.Pp; A.Lp = l.Lp;
+    A.nnz_max = l.nnz_max; A.Mxmax = l.Mxmax; A.Pmax = l.Pmax; A.Pp = l.Pp; A.Lp = l.Lp;
     A.fb = base + l.off_fb;
     A.Mcols = (int32_t*)(base + l.off_M);
     A.Lrows = A.Mcols + chunk;
     A.act = (int16_t*)(base + l.off_act);
-    A.Ew = (double2*)(base + l.off_Ew);
+    A.X = (double*)(base + l.off_X);
     A.R = (double2*)(base + l.off_R);
     A.x = (double2*)(base + l.off_x);
     A.status = status;
@@ -674,8 +845,8 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         if (adapt == 0) LAUNCH(KC_BASIS, st, k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A));
         else LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
         SolveArgs S;
-        S.Ew = A.Ew; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
-        S.nf = A.nf; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
+        S.X = A.X; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
+        S.nf = A.nf; S.Mxmax = l.Mxmax; S.dc = 1; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
         int rc = eaqhm_launch_gram_solve(S, st);
         if (rc != EAQHM_OK) return rc;
         LAUNCH(KC_ACCEPT, st, k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
@@ -694,14 +865,15 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
     }
     const int P = 2 * M, Pp = (int)align_up(P, kNb), Lp = (int)align_up(L, 4);
     double *d_s = nullptr, *d_win = nullptr, *d_am = nullptr, *d_fm = nullptr, *d_f0 = nullptr;
-    double2 *d_Ew = nullptr, *d_R = nullptr, *d_x = nullptr;
+    double* d_X = nullptr;
+    double2 *d_R = nullptr, *d_x = nullptr;
     int32_t* d_meta = nullptr;
     int rc = EAQHM_OK;
     auto body = [&]() -> int {
         CUDA_TRY(cudaMalloc(&d_s, L * 8)); CUDA_TRY(cudaMalloc(&d_win, L * 8));
         CUDA_TRY(cudaMemcpy(d_s, s, L * 8, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d_win, win, L * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&d_Ew, (size_t)P * Lp * 16));
+        CUDA_TRY(cudaMalloc(&d_X, (size_t)2 * M * Lp * 8));
         CUDA_TRY(cudaMalloc(&d_R, (size_t)(P + 1) * Pp * 16));
         CUDA_TRY(cudaMemset(d_R, 0, (size_t)(P + 1) * Pp * 16));
         CUDA_TRY(cudaMalloc(&d_x, (size_t)P * 16));
@@ -712,17 +884,17 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
         if (f0range) {
             CUDA_TRY(cudaMalloc(&d_f0, M * 8));
             CUDA_TRY(cudaMemcpy(d_f0, f0range, M * 8, cudaMemcpyHostToDevice));
-            LAUNCH(KC_BASIS, 0, k_basis_harmonic_explicit<<<1, 256>>>(d_s, d_f0, d_win, L, M, fs, d_Ew, Lp, Rb));
+            LAUNCH(KC_BASIS, 0, k_basis_harmonic_explicit<<<1, 256>>>(d_s, d_f0, d_win, L, M, fs, d_X, Lp, Rb));
         } else {
             CUDA_TRY(cudaMalloc(&d_am, (size_t)L * M * 8)); CUDA_TRY(cudaMalloc(&d_fm, (size_t)L * M * 8));
             CUDA_TRY(cudaMemcpy(d_am, am, (size_t)L * M * 8, cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMemcpy(d_fm, fm, (size_t)L * M * 8, cudaMemcpyHostToDevice));
             CHECK_ARG((size_t)8 * Lp * 8 <= 48 * 1024);
-            LAUNCH(KC_BASIS, 0, k_basis_explicit<<<1, 256, (size_t)8 * Lp * 8>>>(d_s, d_am, d_fm, d_win, L, M, fs, d_Ew, Lp, Rb));
+            LAUNCH(KC_BASIS, 0, k_basis_explicit<<<1, 256, (size_t)8 * Lp * 8>>>(d_s, d_am, d_fm, d_win, L, M, fs, d_X, Lp, Rb));
         }
         SolveArgs S;
-        S.Ew = d_Ew; S.R = d_R; S.x = d_x; S.Mcols = d_meta; S.Lrows = d_meta + 1;
-        S.nf = 1; S.Pmax = P; S.Pp = Pp; S.Lp = Lp; S.status = d_meta + 2;
+        S.X = d_X; S.R = d_R; S.x = d_x; S.Mcols = d_meta; S.Lrows = d_meta + 1;
+        S.nf = 1; S.Mxmax = M; S.dc = 0; S.Pmax = P; S.Pp = Pp; S.Lp = Lp; S.status = d_meta + 2;
         int r2 = eaqhm_launch_gram_solve(S, 0);
         if (r2 != EAQHM_OK) return r2;
         CUDA_TRY(cudaDeviceSynchronize());
@@ -738,7 +910,7 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
     };
     rc = body();
     cudaFree(d_s); cudaFree(d_win); cudaFree(d_am); cudaFree(d_fm); cudaFree(d_f0);
-    cudaFree(d_Ew); cudaFree(d_R); cudaFree(d_x); cudaFree(d_meta);
+    cudaFree(d_X); cudaFree(d_R); cudaFree(d_x); cudaFree(d_meta);
     return rc;
 }
 

@@ -81,17 +81,18 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // ---- analysis stage internals (analysis.cu) -------------------------------------------
 struct AnaLayout {
-    int32_t nnz_max, Mmax, Pmax, Pp, Lp;   // Mmax = 2*nnz_max+1, Pmax = 2*Mmax, Pp = row pitch of R, Lp = pitch of Ew rows
-    int64_t off_fb, off_M, off_act, off_Ew, off_R, off_x, total;
+    int32_t nnz_max, Mxmax, Pmax, Pp, Lp;  // Mxmax = 2*nnz_max generic columns, Pmax = 2*Mxmax+2, Pp = row pitch of R, Lp = pitch of X rows
+    int64_t off_fb, off_M, off_act, off_X, off_R, off_x, total;
 };
 AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max);
 
-// Solves `nf` already-built frames: Ew [nf][Pmax][Lp], Mcols[nf], Nhalf given per frame through the
-// tables (or Lfix>0 for the seams).  Fills R, runs the Cholesky solve, leaves x [nf][Pmax].
+// Solves `nf` already-built frames: X [nf][2][Mxmax][Lp] (windowed basis planes), Mcols[nf] generic
+// columns, Lrows[nf] window samples; dc = 1 when the DC rows (and the rhs row) were written by the basis
+// kernel.  Fills R (P = 2*Mcols + 2*dc), runs the Cholesky solve, leaves x [nf][Pmax].
 struct SolveArgs {
-    const double2* Ew; double2* R; double2* x; const int32_t* Mcols;
-    const int32_t* Lrows;   // [nf] number of window samples per frame
-    int32_t nf, Pmax, Pp, Lp;
+    const double* X; double2* R; double2* x; const int32_t* Mcols;
+    const int32_t* Lrows;
+    int32_t nf, Mxmax, dc, Pmax, Pp, Lp;
     int32_t* status;
 };
 int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st);

@@ -11,60 +11,96 @@ __constant__ double c_cp[kCpTab];
 
 __device__ __forceinline__ double cp_at(int i) { return c_cp[i < kCpTab ? i : kCpTab - 1]; }
 
-// Second derivatives ("moments") of the not-a-knot cubic spline through n >= 4 uniformly spaced
-// knots y[0..n) with spacing h (what interp1d(kind=3) == make_interp_spline(k=3) builds;
-// functions.py:340,367).  Sequential Thomas solve of the reduced system; m may alias nothing.
-__device__ void spline_moments(const double* __restrict__ y, double* __restrict__ m, int n, double h) {
-    auto rhs = [&](int j) {   // 6 (d_j - d_{j-1}) / h
+// Second derivatives ("moments") of the not-a-knot cubic spline through uniformly spaced knots (what
+// interp1d(kind=3) == make_interp_spline(k=3) builds; functions.py:340,367).  Reduced system: with
+// M_0 = 2 M_1 - M_2 the first interior equation gives M_1 = r_1/6 (same at the far end); the remaining
+// unknowns obey M_{j-1} + 4 M_j + M_{j+1} = r_j, r_j = 6 (d_j - d_{j-1}) / h.
+//
+// Parallel form: the influence of a right-hand side decays like (2 - sqrt(3))^distance = 0.268^d, so a
+// thread that owns a chunk of kChunk knots solves the system on its chunk extended by kHalo knots on each
+// side (with an arbitrary Dirichlet value at an artificial cut); 0.268^30 = 7e-18 is below the rounding of the
+// sequential solve.  True run ends inside the window get the exact not-a-knot closure.
+constexpr int kChunk = 32;
+constexpr int kHalo = 30;
+constexpr int kLocalMax = kChunk + 2 * (kHalo + 2) + 4;
+
+template <class Acc>
+__device__ void chunk_moments(const double* __restrict__ y, double* __restrict__ m, int g0, int gend, int a, int b,
+                              double h, Acc acc) {
+    auto rhs = [&](int j) {
         const double d0 = (y[j] - y[j - 1]) / h, d1 = (y[j + 1] - y[j]) / h;
         return 6.0 * (d1 - d0) / h;
     };
-    const double m1 = rhs(1) / 6.0, mn2 = rhs(n - 2) / 6.0;
-    m[1] = m1;
-    m[n - 2] = mn2;
-    const int q0 = 2, q1 = n - 3;           // interior unknowns
-    if (q1 >= q0) {
-        double dprev = 0.0;
-        for (int q = q0; q <= q1; q++) {
-            double r = rhs(q);
-            if (q == q0) r -= m1;
-            if (q == q1) r -= mn2;
-            const double d = (q == q0) ? r * 0.25 : (r - dprev) * cp_at(q - q0);
-            m[q] = d;
-            dprev = d;
+    double loc[kLocalMax];
+    const int lo_lim = max(g0, a - kHalo - 2), hi_lim = min(gend, b + kHalo + 2);
+    int q = a;
+    while (q < b) {
+        if (!acc(q)) { q++; continue; }
+        int ls = q;
+        while (ls > lo_lim && acc(ls - 1)) ls--;
+        const bool true_left = (ls == g0) || !acc(ls - 1);
+        int re = q + 1;
+        while (re < hi_lim && acc(re)) re++;
+        const bool true_right = (re == gend) || !acc(re);
+        if (!(true_left && true_right && re - ls < 4)) {
+            const double B0 = true_left ? rhs(ls + 1) / 6.0 : 0.0;
+            const double B1 = true_right ? rhs(re - 2) / 6.0 : 0.0;
+            const int u0 = true_left ? ls + 2 : ls, u1 = true_right ? re - 3 : re - 1;
+            if (true_left) loc[1] = B0;
+            if (true_right) loc[re - 2 - ls] = B1;
+            double dprev = 0.0;
+            for (int j = u0; j <= u1; j++) {
+                double r = rhs(j);
+                if (j == u0) r -= B0;
+                if (j == u1) r -= B1;
+                const double d = (j == u0) ? r * 0.25 : (r - dprev) * cp_at(j - u0);
+                loc[j - ls] = d;
+                dprev = d;
+            }
+            for (int j = u1 - 1; j >= u0; j--) loc[j - ls] = loc[j - ls] - cp_at(j - u0) * loc[j + 1 - ls];
+            if (true_left) loc[0] = 2.0 * loc[1] - loc[2];
+            if (true_right) loc[re - 1 - ls] = 2.0 * loc[re - 2 - ls] - loc[re - 3 - ls];
+            for (int j = max(ls, a); j < min(re, b); j++) m[j] = loc[j - ls];
         }
-        for (int q = q1 - 1; q >= q0; q--) m[q] = m[q] - cp_at(q - q0) * m[q + 1];
+        q = re;
     }
-    m[0] = 2.0 * m[1] - m[2];
-    m[n - 1] = 2.0 * m[n - 2] - m[n - 3];
 }
 
-// one thread per (harmonic k, utterance u): runs of >= 4 consecutive accepted frames get moments
-__global__ void k_run_moments(eaqhm_tables t, eaqhm_knots kn, double* mom) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= t.Kmax * t.U) return;
-    const int k = idx / t.U, u = idx % t.U;
-    if (!t.active[u]) return;
-    const int g0 = t.gfirst[u], n = t.gcount[u];
-    const double* am = kn.am + (int64_t)k * t.G + g0;
-    const double* fm = kn.fm + (int64_t)k * t.G + g0;
-    double* mo = mom + (int64_t)k * t.G + g0;
+// one thread per (harmonic k, chunk of frames): moments of the frequency spline of every run of >= 4 knots
+__global__ void __launch_bounds__(128) k_run_moments(eaqhm_tables t, eaqhm_knots kn, double* mom) {
+    const int k = blockIdx.y;
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) * kChunk;
+    if (a >= t.G) return;
+    const double* am = kn.am + (int64_t)k * t.G;
+    const double* fm = kn.fm + (int64_t)k * t.G;
+    double* mo = mom + (int64_t)k * t.G;
     const double h = (double)t.step;
-    int i = 0;
-    while (i < n) {
-        if (am[i] == 0.0) { i++; continue; }
-        const int st = i;
-        while (i < n && am[i] != 0.0) i++;
-        if (i - st >= 4) spline_moments(fm + st, mo + st, i - st, h);
+    // a chunk may straddle utterances: handle each utterance's part separately
+    int q = a;
+    const int bend = min(a + kChunk, t.G);
+    while (q < bend) {
+        const int u = t.utt[q];
+        const int g0 = t.gfirst[u], gend = g0 + t.gcount[u];
+        const int b = min(bend, gend);
+        if (t.active[u]) chunk_moments(fm, mo, g0, gend, q, b, h, [&](int j) { return am[j] != 0.0; });
+        q = b;
     }
 }
 
 // DC spline through ALL frames of an utterance (functions.py:340)
-__global__ void k_a0_moments(eaqhm_tables t, const double* a0k, double* a0mom) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= t.U || !t.active[u]) return;
-    const int g0 = t.gfirst[u], n = t.gcount[u];
-    if (n >= 4) spline_moments(a0k + g0, a0mom + g0, n, (double)t.step);
+__global__ void __launch_bounds__(128) k_a0_moments(eaqhm_tables t, const double* a0k, double* a0mom) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) * kChunk;
+    if (a >= t.G) return;
+    const double h = (double)t.step;
+    int q = a;
+    const int bend = min(a + kChunk, t.G);
+    while (q < bend) {
+        const int u = t.utt[q];
+        const int g0 = t.gfirst[u], gend = g0 + t.gcount[u];
+        const int b = min(bend, gend);
+        if (t.active[u]) chunk_moments(a0k, a0mom, g0, gend, q, b, h, [](int) { return true; });
+        q = b;
+    }
 }
 
 // numpy.unwrap applied to one difference (period 2*pi), returned as the corrected difference
@@ -244,9 +280,10 @@ extern "C" int eaqhm_interpolate(const eaqhm_tables* tab, const eaqhm_knots* kno
     int rc = ensure_cp_table();
     if (rc != EAQHM_OK) return rc;
     double* mom = (double*)work;
-    const int nt = tab->Kmax * tab->U;
-    LAUNCH(KC_RUN_MOMENTS, st, k_run_moments<<<(nt + 31) / 32, 32, 0, st>>>(*tab, *knots, mom));
-    LAUNCH(KC_A0_MOMENTS, st, k_a0_moments<<<(tab->U + 31) / 32, 32, 0, st>>>(*tab, knots->a0, a0mom));
+    const int nchunk = (tab->G + kChunk - 1) / kChunk;
+    dim3 gm((nchunk + 127) / 128, tab->Kmax);
+    LAUNCH(KC_RUN_MOMENTS, st, k_run_moments<<<gm, 128, 0, st>>>(*tab, *knots, mom));
+    LAUNCH(KC_A0_MOMENTS, st, k_a0_moments<<<(nchunk + 127) / 128, 128, 0, st>>>(*tab, knots->a0, a0mom));
     dim3 grid((tab->G + 127) / 128, tab->Kmax);
     LAUNCH(KC_INTERP, st, k_interp<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin));
     return EAQHM_OK;
