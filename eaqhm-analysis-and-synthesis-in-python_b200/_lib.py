@@ -28,7 +28,8 @@ class Tables(C.Structure):
                 ("pos", C.c_void_p), ("own", C.c_void_p), ("utt", C.c_void_p), ("N", C.c_void_p),
                 ("K0", C.c_void_p), ("f0", C.c_void_p), ("ustart", C.c_void_p), ("ulen", C.c_void_p),
                 ("gfirst", C.c_void_p), ("gcount", C.c_void_p), ("f0stale", C.c_void_p),
-                ("f0min", C.c_void_p), ("active", C.c_void_p), ("alist", C.c_void_p), ("nA", C.c_int32)]
+                ("f0min", C.c_void_p), ("active", C.c_void_p), ("stat_lo", C.c_void_p), ("stat_hi", C.c_void_p),
+                ("alist", C.c_void_p), ("nA", C.c_int32)]
 
 
 class Tracks(C.Structure):

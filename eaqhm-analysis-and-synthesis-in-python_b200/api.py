@@ -86,9 +86,12 @@ def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', s
     if fc > 0:
         s = preprocess.ellipFilter(s, fs, fc)                                 # functions.py:90-91
     f0min, f0max = host.gender_limits(gender)
+    grid = np.arange(0, len(s) - 1, round(fs * 5 / 1000)) / fs                # functions.py:113
     if f0s is None:
         f0s = preprocess.swipep(s, fs, [f0min, f0max])                        # functions.py:111
-    f0s = preprocess.getLinear(np.asarray(f0s, float), np.arange(0, len(s) - 1, round(fs * 5 / 1000)) / fs)   # :113
+    f0s = np.asarray(f0s, float)
+    if not (len(f0s) == len(grid) and np.array_equal(f0s[:, 0], grid)):       # already on the 5 ms grid?
+        f0s = preprocess.getLinear(f0s, grid)
     if frames is None:
         speech5, voiced5, frame_step = preprocess.voicedUnvoicedFrames(s, fs, gender)   # functions.py:125
     else:

@@ -559,105 +559,126 @@ __global__ void __launch_bounds__(128, 3) k_gram(SolveArgs A) {
 
 // ---------------------------------------------------------------------------------------
 // Cholesky of the augmented matrix [[R, b],[b^H, .]] (left-looking, block width 16) followed by
-// the back substitution L^H x = y.  Replaces inv(R) @ b (functions.py:465,530).  v1: one CTA per
-// frame, one thread per matrix row, DFMA.
+// the back substitution L^H x = y.  Replaces inv(R) @ b (functions.py:465,530).
+// One CTA of 4 warps per frame, several CTAs per SM.  Per block column jb:
+//   phase 1  W = R[jb:, jb:jb+16] - L[jb:, :jb] L[jb:jb+16, :jb]^H  on the FP64 tensor path (DMMA), each warp
+//            a 16x16 tile, fragments read straight from the factor (L2/L1 resident, 16 B per lane);
+//   phase 2  the 16x16 diagonal block is factored in shared memory;
+//   phase 3  rows below: W_i <- W_i L_jj^{-H}, one thread per row.
+// Row P of the augmented matrix carries conj(b); after the factorisation it holds y^H with L y = b.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_chol_solve(SolveArgs A) {
-    const int jl = blockIdx.x, tid = threadIdx.x;
+constexpr int kCholThreads = 128;
+
+__global__ void __launch_bounds__(kCholThreads, 4) k_chol_solve(SolveArgs A) {
+    const int jl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
     const int P = 2 * A.Mcols[jl] + 2 * A.dc;
     double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
     const int Pp = A.Pp;
-    __shared__ double2 Bk[kNb][kNb + 1];     // L[jb+c][kb+k]
     __shared__ double2 D[kNb][kNb + 1];      // diagonal block
-    __shared__ double2 red[16][17];
+    __shared__ double2 red[8][17];
     __shared__ int bad;
     extern __shared__ __align__(16) double2 xs[];   // [Pmax] solution
     if (tid == 0) bad = 0;
 
     for (int jb = 0; jb < P; jb += kNb) {
         const int nbc = min(kNb, P - jb);
-        // phase 1: rows i in [jb, P]: W_i = R[i][jb..] - sum_kb L[i][kb..] L[jb..][kb..]^H
-        const int nrows = P + 1 - jb;
-        const int npass = (nrows + 255) / 256;
-        for (int pass = 0; pass < npass; pass++) {
-            const int i = jb + tid + pass * 256;
-            const bool live = i <= P;
-            double2 W[kNb];
-            if (live) {
+        // ---- phase 1: DMMA update of the block column -------------------------------------------
+        if (jb > 0) {
+            const int ntile = (P + 1 - jb + 15) / 16;
+            for (int t = warp; t < ntile; t += kCholThreads / 32) {
+                const int i0 = jb + 16 * t;
+                double wr[2][2][2], wi[2][2][2];
 #pragma unroll
-                for (int c = 0; c < kNb; c++)
-                    W[c] = (c < nbc && jb + c <= i) ? RF[(size_t)i * Pp + jb + c] : make_double2(0.0, 0.0);
-            }
-            for (int kb = 0; kb < jb; kb += kNb) {
-                __syncthreads();
-                {
-                    const int c = tid >> 4, k = tid & 15;
-                    Bk[c][k] = (c < nbc) ? RF[(size_t)(jb + c) * Pp + kb + k] : make_double2(0.0, 0.0);
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++) wr[a][b][0] = wr[a][b][1] = wi[a][b][0] = wi[a][b][1] = 0.0;
+                const double2* arow[2];
+                const double2* brow[2];
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++) {
+                    arow[s2] = RF + (size_t)min(i0 + s2 * 8 + lr, P) * Pp + lc;
+                    brow[s2] = RF + (size_t)min(jb + s2 * 8 + lr, P) * Pp + lc;
                 }
-                __syncthreads();
-                if (live) {
-                    const double2* Li = RF + (size_t)i * Pp + kb;
 #pragma unroll 4
-                    for (int k = 0; k < kNb; k++) {
-                        const double2 l = Li[k];
+                for (int k0 = 0; k0 < jb; k0 += 4) {
+                    double2 a[2], b[2];
 #pragma unroll
-                        for (int c = 0; c < kNb; c++) cfms_conj_b(W[c], l, Bk[c][k]);
-                    }
+                    for (int s2 = 0; s2 < 2; s2++) { a[s2] = arow[s2][k0]; b[s2] = brow[s2][k0]; }
+#pragma unroll
+                    for (int si = 0; si < 2; si++)
+#pragma unroll
+                        for (int sj = 0; sj < 2; sj++) {
+                            // W -= a * conj(b):  Wr -= ar br + ai bi ; Wi -= ai br - ar bi
+                            dmma884(wr[si][sj], -a[si].x, b[sj].x);
+                            dmma884(wi[si][sj], -a[si].y, b[sj].x);
+                            dmma884(wr[si][sj], -a[si].y, b[sj].y);
+                            dmma884(wi[si][sj], a[si].x, b[sj].y);
+                        }
                 }
-            }
-            if (live) {
 #pragma unroll
-                for (int c = 0; c < kNb; c++) if (c < nbc && jb + c <= i) RF[(size_t)i * Pp + jb + c] = W[c];
+                for (int si = 0; si < 2; si++)
+#pragma unroll
+                    for (int sj = 0; sj < 2; sj++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int i = i0 + si * 8 + lr, cidx = sj * 8 + 2 * lc + e;
+                            if (i <= P && cidx < nbc && jb + cidx <= i) {
+                                double2* p = RF + (size_t)i * Pp + jb + cidx;
+                                double2 v = *p;
+                                v.x += wr[si][sj][e]; v.y += wi[si][sj][e];
+                                *p = v;
+                            }
+                        }
             }
+            __syncthreads();
+        }
+        // ---- phase 2: factor the diagonal block -------------------------------------------------
+        for (int e = tid; e < kNb * kNb; e += kCholThreads) {
+            const int r = e >> 4, c2 = e & 15;
+            D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : make_double2(0.0, 0.0);
         }
         __syncthreads();
-        // phase 2: factor the diagonal block
-        {
-            const int r = tid >> 4, c2 = tid & 15;
-            D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : make_double2(0.0, 0.0);
-            __syncthreads();
-            for (int c = 0; c < nbc; c++) {
-                if (tid == 0) {
-                    const double d = D[c][c].x;
-                    if (!(d > 0.0)) bad = 1;
-                    D[c][c] = make_double2(sqrt(d), 0.0);
-                }
-                __syncthreads();
-                if (c2 == c && r > c && r < nbc) {
-                    const double inv = 1.0 / D[c][c].x;
-                    D[r][c].x *= inv; D[r][c].y *= inv;
-                }
-                __syncthreads();
-                if (r > c && r < nbc && c2 > c && c2 <= r) cfms_conj_b(D[r][c2], D[r][c], D[c2][c]);
-                __syncthreads();
+        for (int c = 0; c < nbc; c++) {
+            if (tid == 0) {
+                const double d = D[c][c].x;
+                if (!(d > 0.0)) bad = 1;
+                D[c][c] = make_double2(sqrt(d), 0.0);
             }
+            __syncthreads();
+            if (tid > c && tid < nbc) {
+                const double inv = 1.0 / D[c][c].x;
+                D[tid][c].x *= inv; D[tid][c].y *= inv;
+            }
+            __syncthreads();
+            for (int e = tid; e < kNb * kNb; e += kCholThreads) {
+                const int r = e >> 4, c2 = e & 15;
+                if (r > c && r < nbc && c2 > c && c2 <= r) cfms_conj_b(D[r][c2], D[r][c], D[c2][c]);
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < kNb * kNb; e += kCholThreads) {
+            const int r = e >> 4, c2 = e & 15;
             if (r < nbc && c2 <= r) RF[(size_t)(jb + r) * Pp + jb + c2] = D[r][c2];
         }
-        __syncthreads();
-        // phase 3: rows below the diagonal block: W_i <- W_i L_jj^{-H}
-        {
-            const int nrows3 = P + 1 - (jb + nbc);
-            const int npass3 = (nrows3 + 255) / 256;
-            for (int pass = 0; pass < npass3; pass++) {
-                const int i = jb + nbc + tid + pass * 256;
-                if (i <= P) {
-                    double2 W[kNb];
+        // ---- phase 3: rows below the diagonal block: W_i <- W_i L_jj^{-H} ---------------------------
+        for (int i = jb + nbc + tid; i <= P; i += kCholThreads) {
+            double2 W[kNb];
+            double2* rowp = RF + (size_t)i * Pp + jb;
 #pragma unroll
-                    for (int c = 0; c < kNb; c++) W[c] = (c < nbc) ? RF[(size_t)i * Pp + jb + c] : make_double2(0.0, 0.0);
+            for (int c = 0; c < kNb; c++) W[c] = (c < nbc) ? rowp[c] : make_double2(0.0, 0.0);
 #pragma unroll
-                    for (int c = 0; c < kNb; c++) {
-                        if (c < nbc) {
-                            double2 v = W[c];
+            for (int c = 0; c < kNb; c++) {
+                if (c < nbc) {
+                    double2 v = W[c];
 #pragma unroll
-                            for (int cc = 0; cc < kNb; cc++) if (cc < c) cfms_conj_b(v, W[cc], D[c][cc]);
-                            const double inv = 1.0 / D[c][c].x;
-                            W[c] = make_double2(v.x * inv, v.y * inv);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < kNb; c++) if (c < nbc) RF[(size_t)i * Pp + jb + c] = W[c];
+                    for (int cc = 0; cc < kNb; cc++) if (cc < c) cfms_conj_b(v, W[cc], D[c][cc]);
+                    const double inv = 1.0 / D[c][c].x;
+                    W[c] = make_double2(v.x * inv, v.y * inv);
                 }
             }
+#pragma unroll
+            for (int c = 0; c < kNb; c++) if (c < nbc) rowp[c] = W[c];
         }
         __syncthreads();
     }
@@ -669,7 +690,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(SolveArgs A) {
         const int c = tid & 15, rr = tid >> 4;
         double2 part = make_double2(0.0, 0.0);
         if (c < nbc)
-            for (int i = jb + nbc + rr; i < P; i += 16) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
+            for (int i = jb + nbc + rr; i < P; i += kCholThreads / 16) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
         red[rr][c] = part;
         __syncthreads();
         if (tid < 32) {
@@ -677,7 +698,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(SolveArgs A) {
             if (tid < nbc) {
                 const double2 yq = RF[(size_t)P * Pp + jb + tid];
                 v = make_double2(yq.x, -yq.y);
-                for (int r2 = 0; r2 < 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
+                for (int r2 = 0; r2 < kCholThreads / 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
             }
             for (int cc = nbc - 1; cc >= 0; cc--) {
                 double2 xc = make_double2(0.0, 0.0);
@@ -698,7 +719,7 @@ __global__ void __launch_bounds__(256) k_chol_solve(SolveArgs A) {
         __syncthreads();
     }
     double2* xo = A.x + (size_t)jl * A.Pmax;
-    for (int p = tid; p < P; p += 256) xo[p] = xs[p];
+    for (int p = tid; p < P; p += kCholThreads) xo[p] = xs[p];
     if (tid == 0 && bad && A.status) atomicAdd(&A.status[0], 1);
 }
 
@@ -781,7 +802,7 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st) {
     dim3 grid(Tt * (Tt + 1) / 2, a.nf);
     LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
-    LAUNCH(KC_CHOL, st, k_chol_solve<<<a.nf, 256, xs_bytes, st>>>(a));
+    LAUNCH(KC_CHOL, st, k_chol_solve<<<a.nf, kCholThreads, xs_bytes, st>>>(a));
     return EAQHM_OK;
 }
 

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kSynThreads) k_synth(eaqhm_tables t, eaqhm_tra
         }
         const double v = a0_at(t, a0k, a0mom, u, n) + 2.0 * acc;
         s_hat[x] = v;
-        e = det[x] - v;
+        if (n >= t.stat_lo[u] && n < t.stat_hi[u]) e = det[x] - v;
     }
     const double bs = block_sum(e, sh);
     if (threadIdx.x == 0) part[(int64_t)u * nblk + blockIdx.x] = bs;
@@ -64,7 +64,7 @@ __global__ void k_reduce_parts(eaqhm_tables t, const double* part, int nblk, dou
     double v = 0.0;
     for (int b = threadIdx.x; b < nb; b += blockDim.x) v += part[(int64_t)u * nblk + b];
     const double r = block_sum(v, sh);
-    if (threadIdx.x == 0) out[u] = divide ? r / (double)t.ulen[u] : r;
+    if (threadIdx.x == 0) out[u] = divide ? r / (double)(t.stat_hi[u] - t.stat_lo[u]) : r;
 }
 
 // second pass of the population variance (numpy.std is two-pass, functions.py:388)
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kSynThreads) k_var_pass(eaqhm_tables t, const 
     const int64_t len = t.ulen[u], us = t.ustart[u];
     const int64_t n = (int64_t)blockIdx.x * kSynThreads + threadIdx.x;
     double q = 0.0;
-    if (n < len) {
+    if (n < len && n >= t.stat_lo[u] && n < t.stat_hi[u]) {
         const double d = (det[us + n] - s_hat[us + n]) - mean[u];
         q = d * d;
     }
@@ -117,19 +117,20 @@ extern "C" int64_t eaqhm_synth_work_bytes(int64_t maxlen, int32_t U) {
 }
 
 extern "C" int eaqhm_synthesize(const eaqhm_tables* tab, const eaqhm_tracks* tr, const double* a0k,
-                                const double* a0mom, const double* det, double* s_hat, double* var_out,
+                                const double* a0mom, const double* det, double* s_hat, double* stat_out,
                                 void* work, int64_t work_bytes, void* stream) {
-    CHECK_ARG(tab && tr && a0k && a0mom && det && s_hat && var_out && work);
+    CHECK_ARG(tab && tr && a0k && a0mom && det && s_hat && stat_out && work);
     CHECK_ARG(tab->maxlen > 0 && work_bytes >= eaqhm_synth_work_bytes(tab->maxlen, tab->U));
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = synth_nblk(tab->maxlen);   // blocks past a shorter utterance's end contribute zero
     double* part = (double*)work;
-    double* mean = part + (int64_t)tab->U * nblk;
+    double* mean = stat_out;
+    double* m2 = stat_out + tab->U;
     dim3 grid(nblk, tab->U);
     LAUNCH(KC_SYNTH, st, k_synth<<<grid, kSynThreads, 0, st>>>(*tab, *tr, a0k, a0mom, det, s_hat, part, nblk));
     LAUNCH(KC_REDUCE, st, k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, mean, true));
     LAUNCH(KC_VARPASS, st, k_var_pass<<<grid, kSynThreads, 0, st>>>(*tab, det, s_hat, mean, part, nblk));
-    LAUNCH(KC_REDUCE, st, k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, var_out, true));
+    LAUNCH(KC_REDUCE, st, k_reduce_parts<<<tab->U, kSynThreads, 0, st>>>(*tab, part, nblk, m2, false));
     return EAQHM_OK;
 }
 

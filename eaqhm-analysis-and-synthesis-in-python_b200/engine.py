@@ -27,6 +27,12 @@ class Utterance:
     f0min: float                    # lower pitch limit (functions.py:95-109)
     Kmax: int                       # functions.py:117-120
     det_part: np.ndarray = None     # SRER target (functions.py:138,146); default s
+    # frame-range shards of one long signal (sharding.py): the shards of a signal share `group`, count only
+    # their owned samples `stat_range` in the SRER, and use the whole signal's target std / stale f0 (Q1)
+    group: object = None
+    stat_range: tuple = None
+    group_std_det: float = None
+    f0stale: float = None
 
 
 @dataclass
@@ -53,11 +59,26 @@ def _dev(a, dtype, device):
     return torch.from_numpy(a).to(device, non_blocking=False)
 
 
+def merge_stats(rows):
+    """{group: (n, mean, M2)} from rows (group, n, mean, M2): Chan's pairwise combination of the per-shard
+    population statistics, so that sqrt(M2/n) of a group equals numpy.std over all its samples (functions.py:388)."""
+    acc = {}
+    for g, n, mean, m2 in rows:
+        if g in acc:
+            n0, mean0, m20 = acc[g]
+            nt = n0 + n
+            dlt = mean - mean0
+            acc[g] = (nt, mean0 + dlt * n / nt, m20 + m2 + dlt * dlt * n0 * n / nt)
+        else:
+            acc[g] = (n, mean, m2)
+    return acc
+
+
 class Engine:
     """Holds the device buffers of one batch and runs the adaptation loop."""
 
     def __init__(self, utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32,
-                 device="cuda", chunk=None, scratch_budget_bytes=6 << 30):
+                 device="cuda", chunk=None, scratch_budget_bytes=6 << 30, stats_allgather=None):
         if not torch.cuda.is_available():
             raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
         self.L = _lib.lib()
@@ -93,7 +114,15 @@ class Engine:
         self.t_ulen = _dev(lens, np.int64, d)
         self.t_gfirst = _dev(self.gfirst, np.int32, d)
         self.t_gcount = _dev(cnts, np.int32, d)
-        self.t_f0stale = _dev([f.f0stale for f in self.ft], np.float64, d)
+        self.t_f0stale = _dev([f.f0stale if u.f0stale is None else float(u.f0stale)
+                               for u, f in zip(self.utts, self.ft)], np.float64, d)
+        sr = [(0, f.length) if u.stat_range is None else tuple(u.stat_range) for u, f in zip(self.utts, self.ft)]
+        self.stat_n = np.array([hi - lo for lo, hi in sr], np.float64)
+        self.t_stat_lo = _dev([lo for lo, _ in sr], np.int64, d)
+        self.t_stat_hi = _dev([hi for _, hi in sr], np.int64, d)
+        # SRER groups: utterances (shards) that share one convergence decision (functions.py:388,394-396)
+        self.group = [("u", i) if u.group is None else ("g", u.group) for i, u in enumerate(self.utts)]
+        self.stats_allgather = stats_allgather
         self.t_f0min = _dev([float(u.f0min) for u in self.utts], np.float64, d)
         self.t_active = torch.ones(U, dtype=torch.uint8, device=d)
         self.alists = [self.gfirst[i] + np.flatnonzero(f.analysed).astype(np.int32) for i, f in enumerate(self.ft)]
@@ -101,7 +130,8 @@ class Engine:
         self.s = _dev(cat([np.asarray(u.s, float).reshape(-1) for u in self.utts]), np.float64, d)
         dets = [np.asarray(u.s if u.det_part is None else u.det_part, float).reshape(-1) for u in self.utts]
         self.det = _dev(cat(dets), np.float64, d)
-        self.std_det = np.array([np.std(x) for x in dets])                   # functions.py:161
+        self.std_det = np.array([np.std(x) if u.group_std_det is None else float(u.group_std_det)
+                                 for u, x in zip(self.utts, dets)])          # functions.py:161
         self.nnz_max = int(max(1, max(int(f.K0.max()) for f in self.ft)))
         self.N_max = int(max(1, max(int(f.N.max()) for f in self.ft)))
         K, T, G = self.Kmax, self.T, self.G
@@ -113,7 +143,7 @@ class Engine:
         self.a0mom = torch.zeros(G, **f64)
         self.s_hat = torch.zeros(T, **f64)
         self.s_best = torch.zeros(T, **f64)
-        self.var = torch.zeros(U, **f64)
+        self.stat = torch.zeros(2 * U, **f64)
         self.improved = torch.zeros(U, dtype=torch.uint8, device=d)
         self.status = torch.zeros(2, dtype=torch.int32, device=d)
         self.flops = torch.zeros(3, **f64)
@@ -130,7 +160,7 @@ class Engine:
         t = self.tab
         t.T, t.maxlen, t.G, t.U, t.Kmax, t.step, t.fs = T, int(lens.max()), G, U, K, self.step, float(fs)
         for name in ("pos", "own", "utt", "N", "K0", "f0", "ustart", "ulen", "gfirst", "gcount", "f0stale",
-                     "f0min", "active", "alist"):
+                     "f0min", "active", "stat_lo", "stat_hi", "alist"):
             setattr(t, name, getattr(self, "t_" + name).data_ptr())
         t.nA = 0
         self.c_tr = _lib.Tracks(*[x.data_ptr() for x in self.tr])
@@ -172,12 +202,24 @@ class Engine:
                                             self.iwork.numel(), self._stream()))
 
     def synthesize(self):
-        """Stage C (functions.py:385-388); returns the residual variance per utterance (device tensor)."""
+        """Stage C (functions.py:385-388); returns [mean | M2] of the residual per utterance (device tensor)."""
         _lib.check(self.L.eaqhm_synthesize(C.byref(self.tab), C.byref(self.c_tr), self.kn[3].data_ptr(),
                                            self.a0mom.data_ptr(), self.det.data_ptr(), self.s_hat.data_ptr(),
-                                           self.var.data_ptr(), self.swork.data_ptr(), self.swork.numel(),
+                                           self.stat.data_ptr(), self.swork.data_ptr(), self.swork.numel(),
                                            self._stream()))
-        return self.var
+        return self.stat
+
+    def group_srer(self, stat):
+        """SRER per utterance from the per-utterance (n, mean, M2): utterances of one group (the shards of a
+        long signal, possibly on other ranks) are merged with the pairwise-variance formula."""
+        U = self.U
+        rows = [(self.group[u], self.stat_n[u], stat[u], stat[U + u]) for u in range(U)]
+        if self.stats_allgather is not None:
+            rows = self.stats_allgather(rows)
+        acc = merge_stats(rows)
+        with np.errstate(all="ignore"):
+            return np.array([20 * np.log10(self.std_det[u] / np.sqrt(acc[self.group[u]][2] / acc[self.group[u]][0]))
+                             for u in range(U)])                          # functions.py:388
 
     def snapshot(self, improved):
         self.improved.copy_(torch.from_numpy(np.asarray(improved, bool).astype(np.uint8)))
@@ -202,12 +244,13 @@ class Engine:
             frames_solved += nA
             self.analysis(a)
             self.interpolate()
-            var = self.synthesize().cpu().numpy()                           # the one host sync per adaptation
-            self.d2h_bytes += var.nbytes
+            stat = self.synthesize().cpu().numpy()                          # the one host sync per adaptation
+            self.d2h_bytes += stat.nbytes
+            srer_u = self.group_srer(stat)
             improved = np.zeros(U, bool)
             with np.errstate(all="ignore"):
                 for u in np.flatnonzero(active):
-                    srer = 20 * np.log10(self.std_det[u] / np.sqrt(var[u]))  # functions.py:388
+                    srer = srer_u[u]
                     SRER[u].append(srer)
                     if a != 0 and srer <= SRER[u][a - 1]:                   # functions.py:394-396
                         active[u] = False

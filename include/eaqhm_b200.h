@@ -79,6 +79,9 @@ typedef struct {
     const double*  f0stale;  /* [U] f0 of the last analysed frame (quirk Q1, functions.py:310) */
     const double*  f0min;    /* [U] lower pitch limit (functions.py:95-109,321)                */
     const uint8_t* active;   /* [U] 1 = utterance still adapting (converged ones are skipped)  */
+    const int64_t* stat_lo;  /* [U] first local sample counted in the SRER statistics          */
+    const int64_t* stat_hi;  /* [U] one past the last one (whole utterance: 0, ulen; a frame-   */
+                             /*     range shard counts only the samples it owns, not its halo)  */
     const int32_t* alist;    /* [nA] analysed frames (global index g), any order               */
     int32_t        nA;
 } eaqhm_tables;
@@ -136,13 +139,15 @@ int eaqhm_interpolate(const eaqhm_tables* tab, const eaqhm_knots* knots, const e
 
 /* ---------------------------------------------------------------------------
  * Stage C — synthesis and SRER statistics (functions.py:385-388):
- * s_hat = a0 + 2*sum_k am*cos(ph); per utterance the population variance of
- * det - s_hat (two-pass).  var_out [U] receives it; the caller forms
- * 20*log10(std_det/sqrt(var)).  `work`: eaqhm_synth_work_bytes(maxlen, U) bytes.
+ * s_hat = a0 + 2*sum_k am*cos(ph); per utterance, over its statistics range, the mean
+ * of e = det - s_hat and M2 = sum (e - mean)^2 (two-pass).  stat_out [2U]: mean in
+ * [0,U), M2 in [U,2U).  The caller forms 20*log10(std_det/sqrt(M2/n)), combining the
+ * shards of one signal with the pairwise-variance formula.
+ * `work`: eaqhm_synth_work_bytes(maxlen, U) bytes.
  * ------------------------------------------------------------------------- */
 int64_t eaqhm_synth_work_bytes(int64_t maxlen, int32_t U);
 int eaqhm_synthesize(const eaqhm_tables* tab, const eaqhm_tracks* tr, const double* a0k,
-                     const double* a0mom, const double* det, double* s_hat, double* var_out,
+                     const double* a0mom, const double* det, double* s_hat, double* stat_out,
                      void* work, int64_t work_bytes, void* stream);
 
 /* Snapshot of the best adaptation (functions.py:397-402) for utterances with

@@ -284,3 +284,45 @@ def test_fallback_path_matches_reference_and_oracle():
     sel, v = g["frame_sel"], g["det_isVoiced"]
     assert ((res.am[sel][v][:, 0] == 10e-4) == (g["det_am"][v][:, 0] == 10e-4)).all()
     assert (g["det_am"][v][:, 0] == 10e-4).sum() > 0
+
+
+def test_frame_range_shards_equal_monolithic_run():
+    """Config c2 mechanics: a signal analysed as three frame-range shards with halo (one SRER group, shared stale f0)
+    must give the monolithic result: same adaptation count, SRER, waveform and parameters (to rounding: the spline
+    halo truncates 0.268^32 influences and the excerpt-local f0 interpolation rounds differently)."""
+    from eaqhm_b200 import sharding, synthetic
+    inp = synth_inputs(synthetic.config_c2(duration=3.0), maxAdpt=2)
+    mono = run_cuda(inp)
+    res, plan, blk = sharding.analyze_long_signal(inp["s"], inp["fs"], inp["f0s"], inp["voiced5"], inp["frame_step"],
+                                                  inp["f0min"], inp["Kmax"], shard_seconds=1.0, maxAdpt=2)
+    assert len(plan) == 3 and blk == (0, 3)
+    assert len(res.SRER) == len(mono.SRER)
+    assert np.abs(np.array(res.SRER) - np.array(mono.SRER)).max() <= 1e-9
+    assert np.abs(res.s_recon - mono.s_recon).max() <= 1e-9
+    v = mono.isVoiced
+    assert (res.isVoiced == v).all() and ((res.am != 0) == (mono.am != 0)).all()
+    fmax = np.abs(mono.am[v]).max(axis=1, keepdims=True)
+    assert (np.abs(res.am[v] - mono.am[v]) / fmax).max() <= TOL_REL
+    strong = (mono.am[v] > 1e-3 * fmax) & (mono.fm[v] != 0)
+    assert (np.abs(res.fm[v] - mono.fm[v])[strong] / mono.fm[v][strong]).max() <= TOL_REL
+
+
+def test_api_drop_in_on_sa19_with_supplied_preprocessing(tmp_path):
+    """eaQHMAnalysisAndSynthesis (functions.py:35) from a wav path, f0 track and 5 ms flags supplied: the four return
+    values have the reference's shapes and the published SRER."""
+    from scipy.io import wavfile
+    from eaqhm_b200.api import eaQHMAnalysisAndSynthesis
+    g, kw = load_golden("sa19")
+    wav = str(tmp_path / "SA19.WAV")
+    wavfile.write(wav, int(g["fs"]), g["pcm"])
+    s_recon, SRER, det, t = eaQHMAnalysisAndSynthesis(wav, "female", printPrompts=False, loadingScreen=False, f0s=g["f0s"],
+                                                      frames=(g["speech5"], g["voiced5"], int(g["frame_step"])))
+    assert s_recon.shape == (len(g["pcm"]),) and len(SRER) == 6 and t > 0
+    assert np.abs(np.array(SRER) - g["SRER"]).max() <= 1e-8 and np.abs(s_recon - g["s_recon"]).max() <= TOL_S
+    assert len(det) == 4233
+    d = det[2000]
+    assert d.isVoiced and d.ak == [] and d.amplitudes.dtype == object and d.amplitudes[0].shape == (1,)
+    i = int(np.flatnonzero(g["frame_sel"] == 2000)[0])
+    nk = int(g["det_nk"][i])
+    assert len(d.amplitudes) == nk
+    assert abs(float(d.amplitudes[0][0]) - g["det_am"][i, 0]) <= 1e-9 * g["det_am"][i].max()
