@@ -1,6 +1,8 @@
 // Stage A of one eaQHM adaptation: per-frame basis construction, weighted complex Gram,
 // Cholesky solve, frequency mismatch and acceptance (reference: functions.py:176-329,
 // iqhmLS_complexamps :420-470, eaqhmLS_complexamps :472-535).  sm_100a, FP64.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -86,7 +88,7 @@ __global__ void k_active(AnaArgs A) {
         A.Lrows[jl] = 2 * A.t.N[g] + 1;
         if (A.flop_stats) {   // structure-aware minimum work of this frame
             const double M = 2.0 * count + 1.0, L = 2.0 * A.t.N[g] + 1.0, P = 2.0 * M;
-            atomicAdd(&A.flop_stats[0], 12.0 * L * M * M);
+            if (A.adapt > 0) atomicAdd(&A.flop_stats[0], 12.0 * L * M * M);   // adaptation 0 uses the Toeplitz tables
             atomicAdd(&A.flop_stats[1], (4.0 / 3.0) * P * P * P + 8.0 * P * P);
             atomicAdd(&A.flop_stats[2], 16.0 * L * M);
         }
@@ -558,139 +560,215 @@ __global__ void __launch_bounds__(128, 3) k_gram(SolveArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Adaptation 0: the basis is stationary and harmonic, E2[n,h] = exp(j 2 pi h f0 n / fs) (functions.py:453-454),
+// so every Gram entry depends only on the harmonic-number difference d = h_q - h_p:
+//   sum_n n^e w_n^2 exp(j d theta n),  theta = 2 pi f0 / fs,  e = 0,1,2   (Toeplitz blocks).
+// With the symmetric window the three lag tables are T0(d) = w_0^2 + 2 sum_{n>0} w_n^2 cos(d theta n) (real),
+// T1(d) = 2j sum_{n>0} n w_n^2 sin(d theta n) (imaginary, odd), T2(d) = 2 sum_{n>0} n^2 w_n^2 cos(d theta n) (real):
+// O(L K) work instead of the O(L K^2) Gram.  One CTA per frame: thread per lag d (rotation recurrence over n), then
+// the P x P lower triangle is filled from the tables.  The DC rows and the rhs row come from k_basis<false>.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram_toeplitz(AnaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int jl = blockIdx.x;
+    const int g = A.t.alist[A.j0 + jl];
+    const int N = A.t.N[g], L = 2 * N + 1;
+    const int Mx = A.Mcols[jl], K = Mx / 2;
+    double* w2 = reinterpret_cast<double*>(smem_raw);       // [N+1]  w_n^2 for n = 0..N
+    double* T0 = w2 + (A.Lp / 2 + 2);                       // [2K+1]
+    double* T1 = T0 + (A.Mxmax + 1);
+    double* T2 = T1 + (A.Mxmax + 1);
+    for (int n = tid; n <= N; n += 256) {
+        const double nn = (double)(2 * n), den = (double)(L - 1);   // numpy.blackman at index N + n
+        const double wn = 0.42 + 0.5 * cos((kPi * nn) / den) + 0.08 * cos(((2.0 * kPi) * nn) / den);
+        w2[n] = wn * wn;
+    }
+    __syncthreads();
+    const double theta = (kTwoPi * A.t.f0[g]) / A.t.fs;
+    for (int d = tid; d <= 2 * K; d += 256) {
+        double rs, rc;
+        sincos((double)d * theta, &rs, &rc);
+        double zr = 1.0, zi = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int n = 1; n <= N; n++) {
+            const double nzr = zr * rc - zi * rs;
+            zi = zr * rs + zi * rc;
+            zr = nzr;
+            const double wn2 = w2[n], nw = (double)n * wn2;
+            t0 = fma(wn2, zr, t0);
+            t1 = fma(nw, zi, t1);
+            t2 = fma((double)n * nw, zr, t2);
+        }
+        T0[d] = w2[0] + 2.0 * t0;
+        T1[d] = 2.0 * t1;
+        T2[d] = 2.0 * t2;
+    }
+    __syncthreads();
+    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+    const int Pp = A.Pp;
+    // harmonic number of generic column c: +1..+K for c < K, -1..-K for c >= K
+    for (int e = tid; e < Mx * Mx; e += 256) {
+        const int p = e / Mx, q = e - p * Mx;
+        const int hp = p < K ? p + 1 : -(p - K + 1), hq = q < K ? q + 1 : -(q - K + 1);
+        const int d = hq - hp, ad = d < 0 ? -d : d;
+        if (q <= p) {
+            RF[(size_t)p * Pp + q] = make_double2(T0[ad], 0.0);
+            RF[(size_t)(Mx + p) * Pp + Mx + q] = make_double2(T2[ad], 0.0);
+        }
+        RF[(size_t)(Mx + p) * Pp + q] = make_double2(0.0, d < 0 ? -T1[ad] : T1[ad]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Cholesky of the augmented matrix [[R, b],[b^H, .]] (left-looking, block width 16) followed by
 // the back substitution L^H x = y.  Replaces inv(R) @ b (functions.py:465,530).
-// One CTA of 4 warps per frame, several CTAs per SM.  Per block column jb:
-//   phase 1  W = R[jb:, jb:jb+16] - L[jb:, :jb] L[jb:jb+16, :jb]^H  on the FP64 tensor path (DMMA), each warp
-//            a 16x16 tile, fragments read straight from the factor (L2/L1 resident, 16 B per lane);
-//   phase 2  the 16x16 diagonal block is factored in shared memory;
-//   phase 3  rows below: W_i <- W_i L_jj^{-H}, one thread per row.
+// One CTA of kNW warps per frame, several CTAs per SM.  Rows are owned in blocks of 16 by warp
+// (row block % kNW), so a warp only ever rewrites its own rows.  Per block column jb, per owned row block:
+//   1. W = R[rows, jb:jb+16] - L[rows, :jb] L[jb:jb+16, :jb]^H on the FP64 tensor path (DMMA m8n8k4), fragments
+//      read straight from the factor (16 B per lane), result staged in the warp's shared-memory tile;
+//   2. the warp that owns the diagonal block factors it warp-synchronously (no CTA barrier) into D;
+//   3. after ONE CTA barrier ("D ready") every warp finishes its staged tiles: W_i <- W_i L_jj^{-H}, one lane per
+//      row, and writes the final rows; a second barrier closes the block column.
 // Row P of the augmented matrix carries conj(b); after the factorisation it holds y^H with L y = b.
 // ---------------------------------------------------------------------------------------
-constexpr int kCholThreads = 128;
-
-__global__ void __launch_bounds__(kCholThreads, 4) k_chol_solve(SolveArgs A) {
+template <int kNW>
+__global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(SolveArgs A) {
+    constexpr int kThreads = kNW * 32;
     const int jl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane >> 2, lc = lane & 3;
     const int P = 2 * A.Mcols[jl] + 2 * A.dc;
     double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
     const int Pp = A.Pp;
-    __shared__ double2 D[kNb][kNb + 1];      // diagonal block
-    __shared__ double2 red[8][17];
+    __shared__ double2 D[kNb][kNb + 1];               // factored diagonal block of the current block column
+    __shared__ double2 Tall[kNW][kNb][kNb + 1];       // per-warp staging tile
+    __shared__ double2 red[kThreads / 16][17];
     __shared__ int bad;
-    extern __shared__ __align__(16) double2 xs[];   // [Pmax] solution
+    extern __shared__ __align__(16) double2 xs[];     // [Pmax] solution
+    double2 (*T)[kNb + 1] = Tall[warp];
     if (tid == 0) bad = 0;
+    __syncthreads();
 
-    for (int jb = 0; jb < P; jb += kNb) {
-        const int nbc = min(kNb, P - jb);
-        // ---- phase 1: DMMA update of the block column -------------------------------------------
-        if (jb > 0) {
-            const int ntile = (P + 1 - jb + 15) / 16;
-            for (int t = warp; t < ntile; t += kCholThreads / 32) {
-                const int i0 = jb + 16 * t;
+    const int nrb = (P + 1 + kNb - 1) / kNb;          // row blocks (the rhs row P is in the last one)
+    const int ncb = (P + kNb - 1) / kNb;              // block columns
+    for (int jbk = 0; jbk < ncb; jbk++) {
+        const int jb = jbk * kNb, nbc = min(kNb, P - jb);
+        int rb = jbk + ((warp - jbk) % kNW + kNW) % kNW;     // first owned row block >= jbk
+        bool d_ready = false;
+        for (; rb < nrb || !d_ready; rb += kNW) {
+            const bool have = rb < nrb;
+            const int i0 = rb * kNb;
+            if (have) {
+                // ---- 1. DMMA update of the 16x16 tile ---------------------------------------------
                 double wr[2][2][2], wi[2][2][2];
 #pragma unroll
                 for (int a = 0; a < 2; a++)
 #pragma unroll
                     for (int b = 0; b < 2; b++) wr[a][b][0] = wr[a][b][1] = wi[a][b][0] = wi[a][b][1] = 0.0;
-                const double2* arow[2];
-                const double2* brow[2];
+                if (jb > 0) {
+                    const double2* arow[2];
+                    const double2* brow[2];
 #pragma unroll
-                for (int s2 = 0; s2 < 2; s2++) {
-                    arow[s2] = RF + (size_t)min(i0 + s2 * 8 + lr, P) * Pp + lc;
-                    brow[s2] = RF + (size_t)min(jb + s2 * 8 + lr, P) * Pp + lc;
-                }
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        arow[s2] = RF + (size_t)min(i0 + s2 * 8 + lr, P) * Pp + lc;
+                        brow[s2] = RF + (size_t)min(jb + s2 * 8 + lr, P) * Pp + lc;
+                    }
 #pragma unroll 4
-                for (int k0 = 0; k0 < jb; k0 += 4) {
-                    double2 a[2], b[2];
+                    for (int k0 = 0; k0 < jb; k0 += 4) {
+                        double2 a[2], b[2];
 #pragma unroll
-                    for (int s2 = 0; s2 < 2; s2++) { a[s2] = arow[s2][k0]; b[s2] = brow[s2][k0]; }
+                        for (int s2 = 0; s2 < 2; s2++) { a[s2] = arow[s2][k0]; b[s2] = brow[s2][k0]; }
 #pragma unroll
-                    for (int si = 0; si < 2; si++)
+                        for (int si = 0; si < 2; si++)
 #pragma unroll
-                        for (int sj = 0; sj < 2; sj++) {
-                            // W -= a * conj(b):  Wr -= ar br + ai bi ; Wi -= ai br - ar bi
-                            dmma884(wr[si][sj], -a[si].x, b[sj].x);
-                            dmma884(wi[si][sj], -a[si].y, b[sj].x);
-                            dmma884(wr[si][sj], -a[si].y, b[sj].y);
-                            dmma884(wi[si][sj], a[si].x, b[sj].y);
-                        }
+                            for (int sj = 0; sj < 2; sj++) {
+                                // W -= a * conj(b):  Wr -= ar br + ai bi ; Wi -= ai br - ar bi
+                                dmma884(wr[si][sj], -a[si].x, b[sj].x);
+                                dmma884(wi[si][sj], -a[si].y, b[sj].x);
+                                dmma884(wr[si][sj], -a[si].y, b[sj].y);
+                                dmma884(wi[si][sj], a[si].x, b[sj].y);
+                            }
+                    }
                 }
+                __syncwarp();
 #pragma unroll
                 for (int si = 0; si < 2; si++)
 #pragma unroll
                     for (int sj = 0; sj < 2; sj++)
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const int i = i0 + si * 8 + lr, cidx = sj * 8 + 2 * lc + e;
+                            const int r = si * 8 + lr, cidx = sj * 8 + 2 * lc + e, i = i0 + r;
+                            double2 v = make_double2(0.0, 0.0);
                             if (i <= P && cidx < nbc && jb + cidx <= i) {
-                                double2* p = RF + (size_t)i * Pp + jb + cidx;
-                                double2 v = *p;
+                                v = RF[(size_t)i * Pp + jb + cidx];
                                 v.x += wr[si][sj][e]; v.y += wi[si][sj][e];
-                                *p = v;
                             }
+                            T[r][cidx] = v;
                         }
-            }
-            __syncthreads();
-        }
-        // ---- phase 2: factor the diagonal block -------------------------------------------------
-        for (int e = tid; e < kNb * kNb; e += kCholThreads) {
-            const int r = e >> 4, c2 = e & 15;
-            D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        for (int c = 0; c < nbc; c++) {
-            if (tid == 0) {
-                const double d = D[c][c].x;
-                if (!(d > 0.0)) bad = 1;
-                D[c][c] = make_double2(sqrt(d), 0.0);
-            }
-            __syncthreads();
-            if (tid > c && tid < nbc) {
-                const double inv = 1.0 / D[c][c].x;
-                D[tid][c].x *= inv; D[tid][c].y *= inv;
-            }
-            __syncthreads();
-            for (int e = tid; e < kNb * kNb; e += kCholThreads) {
-                const int r = e >> 4, c2 = e & 15;
-                if (r > c && r < nbc && c2 > c && c2 <= r) cfms_conj_b(D[r][c2], D[r][c], D[c2][c]);
-            }
-            __syncthreads();
-        }
-        for (int e = tid; e < kNb * kNb; e += kCholThreads) {
-            const int r = e >> 4, c2 = e & 15;
-            if (r < nbc && c2 <= r) RF[(size_t)(jb + r) * Pp + jb + c2] = D[r][c2];
-        }
-        // ---- phase 3: rows below the diagonal block: W_i <- W_i L_jj^{-H} ---------------------------
-        for (int i = jb + nbc + tid; i <= P; i += kCholThreads) {
-            double2 W[kNb];
-            double2* rowp = RF + (size_t)i * Pp + jb;
-#pragma unroll
-            for (int c = 0; c < kNb; c++) W[c] = (c < nbc) ? rowp[c] : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int c = 0; c < kNb; c++) {
-                if (c < nbc) {
-                    double2 v = W[c];
-#pragma unroll
-                    for (int cc = 0; cc < kNb; cc++) if (cc < c) cfms_conj_b(v, W[cc], D[c][cc]);
-                    const double inv = 1.0 / D[c][c].x;
-                    W[c] = make_double2(v.x * inv, v.y * inv);
+                __syncwarp();
+                // ---- 2. diagonal tile: factor it in place (warp-synchronous), publish as D ----------
+                if (rb == jbk) {
+                    for (int c = 0; c < nbc; c++) {
+                        const double dd = T[c][c].x;
+                        if (!(dd > 0.0) && lane == 0) bad = 1;
+                        const double dsq = sqrt(dd), inv = 1.0 / dsq;
+                        __syncwarp();
+                        if (lane == c) T[c][c] = make_double2(dsq, 0.0);
+                        else if (lane > c && lane < nbc) { T[lane][c].x *= inv; T[lane][c].y *= inv; }
+                        __syncwarp();
+                        for (int e = lane; e < kNb * kNb; e += 32) {
+                            const int r = e >> 4, c2 = e & 15;
+                            if (r > c && r < nbc && c2 > c && c2 <= r) cfms_conj_b(T[r][c2], T[r][c], T[c2][c]);
+                        }
+                        __syncwarp();
+                    }
+                    for (int e = lane; e < kNb * kNb; e += 32) {
+                        const int r = e >> 4, c2 = e & 15;
+                        const double2 v = (r < nbc && c2 <= r) ? T[r][c2] : make_double2(0.0, 0.0);
+                        D[r][c2] = v;
+                        if (r < nbc && c2 <= r) RF[(size_t)(jb + r) * Pp + jb + c2] = v;
+                    }
                 }
             }
+            if (!d_ready) {
+                __syncthreads();                      // D ready (every warp passes here exactly once per block column)
+                d_ready = true;
+            }
+            // ---- 3. rows below the diagonal block: W_i <- W_i L_jj^{-H}, one lane per row ------------
+            if (have && lane < kNb) {
+                const int i = i0 + lane;
+                // rows of the diagonal tile that lie below the (possibly partial) diagonal block - the rhs row P in
+                // the last block column - are ordinary rows
+                if (i <= P && !(rb == jbk && lane < nbc)) {
+                    double2 W[kNb];
 #pragma unroll
-            for (int c = 0; c < kNb; c++) if (c < nbc) rowp[c] = W[c];
+                    for (int c = 0; c < kNb; c++) W[c] = T[lane][c];
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) {
+                        if (c < nbc) {
+                            double2 v = W[c];
+#pragma unroll
+                            for (int cc = 0; cc < kNb; cc++) if (cc < c) cfms_conj_b(v, W[cc], D[c][cc]);
+                            const double inv = 1.0 / D[c][c].x;
+                            W[c] = make_double2(v.x * inv, v.y * inv);
+                        }
+                    }
+                    double2* rowp = RF + (size_t)i * Pp + jb;
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) if (c < nbc) rowp[c] = W[c];
+                }
+            }
+            __syncwarp();
         }
-        __syncthreads();
+        __syncthreads();                              // block column complete: rows final for the next one
     }
 
     // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y
-    const int nblk = (P + kNb - 1) / kNb;
-    for (int b = nblk - 1; b >= 0; b--) {
+    for (int b = ncb - 1; b >= 0; b--) {
         const int jb = b * kNb, nbc = min(kNb, P - jb);
         const int c = tid & 15, rr = tid >> 4;
         double2 part = make_double2(0.0, 0.0);
         if (c < nbc)
-            for (int i = jb + nbc + rr; i < P; i += kCholThreads / 16) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
+            for (int i = jb + nbc + rr; i < P; i += kThreads / 16) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
         red[rr][c] = part;
         __syncthreads();
         if (tid < 32) {
@@ -698,7 +776,7 @@ __global__ void __launch_bounds__(kCholThreads, 4) k_chol_solve(SolveArgs A) {
             if (tid < nbc) {
                 const double2 yq = RF[(size_t)P * Pp + jb + tid];
                 v = make_double2(yq.x, -yq.y);
-                for (int r2 = 0; r2 < kCholThreads / 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
+                for (int r2 = 0; r2 < kThreads / 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
             }
             for (int cc = nbc - 1; cc >= 0; cc--) {
                 double2 xc = make_double2(0.0, 0.0);
@@ -719,7 +797,7 @@ __global__ void __launch_bounds__(kCholThreads, 4) k_chol_solve(SolveArgs A) {
         __syncthreads();
     }
     double2* xo = A.x + (size_t)jl * A.Pmax;
-    for (int p = tid; p < P; p += kCholThreads) xo[p] = xs[p];
+    for (int p = tid; p < P; p += kThreads) xo[p] = xs[p];
     if (tid == 0 && bad && A.status) atomicAdd(&A.status[0], 1);
 }
 
@@ -792,7 +870,7 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
     return l;
 }
 
-int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st) {
+int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     static bool gram_attr = false;
     if (!gram_attr) {
         CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
@@ -800,9 +878,21 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st) {
     }
     const int Tt = (a.Mxmax + kGT - 1) / kGT;
     dim3 grid(Tt * (Tt + 1) / 2, a.nf);
-    LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
+    if (do_gram) LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
-    LAUNCH(KC_CHOL, st, k_chol_solve<<<a.nf, kCholThreads, xs_bytes, st>>>(a));
+    // experiment knob (tools only): EAQHM_CHOL_WARPS in {2,4,8} warps per frame
+    static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
+    static bool chol_attr = false;
+    if (!chol_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        chol_attr = true;
+    }
+    CHECK_ARG(xs_bytes <= 64 * 1024);
+    if (warps == 2) LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a));
+    else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a));
+    else LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a));
     return EAQHM_OK;
 }
 
@@ -868,7 +958,14 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         SolveArgs S;
         S.X = A.X; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
         S.nf = A.nf; S.Mxmax = l.Mxmax; S.dc = 1; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
-        int rc = eaqhm_launch_gram_solve(S, st);
+        static const bool use_toeplitz = !(getenv("EAQHM_NO_TOEPLITZ") && atoi(getenv("EAQHM_NO_TOEPLITZ")));
+        const bool toeplitz = adapt == 0 && use_toeplitz;
+        if (toeplitz) {
+            const size_t tsm = ((size_t)(l.Lp / 2 + 2) + 3 * (size_t)(l.Mxmax + 1)) * 8;
+            CHECK_ARG(tsm <= 48 * 1024);
+            LAUNCH(KC_GRAM, st, k_gram_toeplitz<<<A.nf, 256, tsm, st>>>(A));
+        }
+        int rc = eaqhm_launch_gram_solve(S, st, !toeplitz);
         if (rc != EAQHM_OK) return rc;
         LAUNCH(KC_ACCEPT, st, k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
     }
@@ -916,7 +1013,7 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
         SolveArgs S;
         S.X = d_X; S.R = d_R; S.x = d_x; S.Mcols = d_meta; S.Lrows = d_meta + 1;
         S.nf = 1; S.Mxmax = M; S.dc = 0; S.Pmax = P; S.Pp = Pp; S.Lp = Lp; S.status = d_meta + 2;
-        int r2 = eaqhm_launch_gram_solve(S, 0);
+        int r2 = eaqhm_launch_gram_solve(S, 0, true);
         if (r2 != EAQHM_OK) return r2;
         CUDA_TRY(cudaDeviceSynchronize());
         CUDA_TRY(cudaMemcpy(amp, d_x, (size_t)M * 16, cudaMemcpyDeviceToHost));

@@ -95,7 +95,7 @@ struct SolveArgs {
     int32_t nf, Mxmax, dc, Pmax, Pp, Lp;
     int32_t* status;
 };
-int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st);
+int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram);
 
 // spline helpers shared by interp.cu and synth.cu
 __device__ __forceinline__ double spline_eval(double y0, double y1, double m0, double m1, double h, double t1) {
