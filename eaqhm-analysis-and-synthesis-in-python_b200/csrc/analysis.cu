@@ -762,33 +762,49 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
         __syncthreads();                              // block column complete: rows final for the next one
     }
 
-    // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y
+    // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y.
+    // Per block column (last to first): the diagonal block is brought into shared memory with one coalesced load
+    // (the 16 dependent steps of the triangular solve then never touch global memory), the contribution of the
+    // already solved unknowns is a column-block dot product spread over all threads (independent loads, unrolled).
     for (int b = ncb - 1; b >= 0; b--) {
         const int jb = b * kNb, nbc = min(kNb, P - jb);
         const int c = tid & 15, rr = tid >> 4;
+        for (int e = tid; e < kNb * kNb; e += kThreads) {
+            const int r = e >> 4, c2 = e & 15;
+            D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : make_double2(0.0, 0.0);
+        }
         double2 part = make_double2(0.0, 0.0);
-        if (c < nbc)
-            for (int i = jb + nbc + rr; i < P; i += kThreads / 16) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
+        if (c < nbc) {
+            constexpr int kStride = kThreads / 16;
+            int i = jb + nbc + rr;
+            for (; i + 3 * kStride < P; i += 4 * kStride) {
+                const double2 l0 = RF[(size_t)i * Pp + jb + c], l1 = RF[(size_t)(i + kStride) * Pp + jb + c];
+                const double2 l2 = RF[(size_t)(i + 2 * kStride) * Pp + jb + c], l3 = RF[(size_t)(i + 3 * kStride) * Pp + jb + c];
+                cfma_conj_a(part, l0, xs[i]); cfma_conj_a(part, l1, xs[i + kStride]);
+                cfma_conj_a(part, l2, xs[i + 2 * kStride]); cfma_conj_a(part, l3, xs[i + 3 * kStride]);
+            }
+            for (; i < P; i += kStride) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
+        }
         red[rr][c] = part;
+        const double2 yq = (tid < nbc) ? RF[(size_t)P * Pp + jb + tid] : make_double2(0.0, 0.0);
         __syncthreads();
         if (tid < 32) {
             double2 v = make_double2(0.0, 0.0);
             if (tid < nbc) {
-                const double2 yq = RF[(size_t)P * Pp + jb + tid];
                 v = make_double2(yq.x, -yq.y);
                 for (int r2 = 0; r2 < kThreads / 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
             }
             for (int cc = nbc - 1; cc >= 0; cc--) {
                 double2 xc = make_double2(0.0, 0.0);
                 if (tid == cc) {
-                    const double inv = 1.0 / RF[(size_t)(jb + cc) * Pp + jb + cc].x;
+                    const double inv = 1.0 / D[cc][cc].x;
                     xc = make_double2(v.x * inv, v.y * inv);
                     xs[jb + cc] = xc;
                 }
                 xc.x = __shfl_sync(0xffffffffu, xc.x, cc);
                 xc.y = __shfl_sync(0xffffffffu, xc.y, cc);
                 if (tid < cc) {   // v -= conj(L[jb+cc][jb+tid]) * x_cc
-                    const double2 l = RF[(size_t)(jb + cc) * Pp + jb + tid];
+                    const double2 l = D[cc][tid];
                     v.x -= l.x * xc.x + l.y * xc.y;
                     v.y -= l.x * xc.y - l.y * xc.x;
                 }
@@ -880,19 +896,12 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     dim3 grid(Tt * (Tt + 1) / 2, a.nf);
     if (do_gram) LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
-    // experiment knob (tools only): EAQHM_CHOL_WARPS in {2,4,8} warps per frame
+    // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
-    static bool chol_attr = false;
-    if (!chol_attr) {
-        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        chol_attr = true;
-    }
-    CHECK_ARG(xs_bytes <= 64 * 1024);
-    if (warps == 2) LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a));
-    else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a));
-    else LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a));
+    CHECK_ARG(xs_bytes <= 32 * 1024);
+    if (warps == 1) LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a));
+    else if (warps == 4) LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a));
+    else LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a));
     return EAQHM_OK;
 }
 
