@@ -631,6 +631,13 @@ __global__ void __launch_bounds__(256) k_gram_toeplitz(AnaArgs A) {
 //      row, and writes the final rows; a second barrier closes the block column.
 // Row P of the augmented matrix carries conj(b); after the factorisation it holds y^H with L y = b.
 // ---------------------------------------------------------------------------------------
+#ifdef EAQHM_CHOL_TIMING
+__device__ unsigned long long g_chol_cycles[8];
+#define TMARK(slot) do { if (lane == 0) { const long long _t = clock64(); tacc[slot] += _t - tlast; tlast = _t; } } while (0)
+#else
+#define TMARK(slot) do { } while (0)
+#endif
+
 template <int kNW>
 __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(SolveArgs A) {
     constexpr int kThreads = kNW * 32;
@@ -647,6 +654,10 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
     double2 (*T)[kNb + 1] = Tall[warp];
     if (tid == 0) bad = 0;
     __syncthreads();
+#ifdef EAQHM_CHOL_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
 
     const int nrb = (P + 1 + kNb - 1) / kNb;          // row blocks (the rhs row P is in the last one)
     const int ncb = (P + kNb - 1) / kNb;              // block columns
@@ -690,6 +701,7 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
                     }
                 }
                 __syncwarp();
+                TMARK(0);   // k loop
 #pragma unroll
                 for (int si = 0; si < 2; si++)
 #pragma unroll
@@ -705,6 +717,7 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
                             T[r][cidx] = v;
                         }
                 __syncwarp();
+                TMARK(1);   // staging
                 // ---- 2. diagonal tile: factor it in place (warp-synchronous), publish as D ----------
                 if (rb == jbk) {
                     for (int c = 0; c < nbc; c++) {
@@ -729,10 +742,12 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
                     }
                 }
             }
+            TMARK(2);       // factor
             if (!d_ready) {
                 __syncthreads();                      // D ready (every warp passes here exactly once per block column)
                 d_ready = true;
             }
+            TMARK(3);       // wait D
             // ---- 3. rows below the diagonal block: W_i <- W_i L_jj^{-H}, one lane per row ------------
             if (have && lane < kNb) {
                 const int i = i0 + lane;
@@ -758,8 +773,10 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
                 }
             }
             __syncwarp();
+            TMARK(4);       // solve rows
         }
         __syncthreads();                              // block column complete: rows final for the next one
+        TMARK(5);           // wait end of block column
     }
 
     // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y.
@@ -812,6 +829,10 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
         }
         __syncthreads();
     }
+    TMARK(6);               // back substitution
+#ifdef EAQHM_CHOL_TIMING
+    if (lane == 0) for (int q = 0; q < 8; q++) atomicAdd(&g_chol_cycles[q], (unsigned long long)tacc[q]);
+#endif
     double2* xo = A.x + (size_t)jl * A.Pmax;
     for (int p = tid; p < P; p += kThreads) xo[p] = xs[p];
     if (tid == 0 && bad && A.status) atomicAdd(&A.status[0], 1);
@@ -1052,3 +1073,13 @@ extern "C" int eaqhm_eaqhmLS_complexamps(const double* s, int32_t L, const doubl
     CHECK_ARG(am != nullptr && fm != nullptr);
     return seam_solve(s, L, M, window, fs, am, fm, nullptr, amp, slope);
 }
+
+#ifdef EAQHM_CHOL_TIMING
+extern "C" int eaqhm_debug_chol_cycles(double* out, int reset) {
+    unsigned long long h[8];
+    if (cudaMemcpyFromSymbol(h, g_chol_cycles, sizeof(h)) != cudaSuccess) return EAQHM_E_CUDA;
+    for (int i = 0; i < 8; i++) out[i] = (double)h[i];
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_cycles, z, sizeof(z)); }
+    return EAQHM_OK;
+}
+#endif
