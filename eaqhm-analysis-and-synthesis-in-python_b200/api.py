@@ -78,7 +78,8 @@ def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', s
 
     Keyword-only extensions: ``f0s`` ((n,3) [t,f0,strength] track, replaces SWIPE') and ``frames``
     ((speech5, voiced5, frame_step), replaces voicedUnvoicedFrames) let a caller supply the
-    host preprocessing results; ``loadingScreen`` is accepted and ignored (no per-frame loop).
+    host preprocessing results (by default both are computed on the CPU by preprocess.py like the
+    reference does); ``loadingScreen`` is accepted and ignored (there is no per-frame Python loop).
     """
     from . import preprocess
     startTime = time()

@@ -89,8 +89,123 @@ def voicedUnvoicedFrames(s, fs, gender):
     return medfilt5(isSpeech), medfilt5(isVoiced), step
 
 
-def swipep(x, fs, plim):
-    """SWIPE' pitch track (SWIPE.py:14-132 of the reference, a third-party port).  Host preprocessing outside the hot
-    path; not restated in round 1 — supply the track through ``f0s=``."""
-    raise NotImplementedError("SWIPE' f0 estimation is host preprocessing outside the hot path and is not part of this "
-                              "round; pass f0s=(n,3) [t, f0, strength] to eaQHMAnalysisAndSynthesis")
+def _psd_spectrogram(x, nfft, fs, window, noverlap):
+    """One-sided PSD spectrogram without detrending (what matplotlib.pyplot.specgram(mode='psd') returns and
+    SWIPE.py:66 consumes): |X|^2 scaled by 1/(fs*sum(w^2)), doubled except at DC and Nyquist; frame times are the
+    window centres."""
+    hop = nfft - noverlap
+    nseg = (len(x) - noverlap) // hop
+    idx = np.arange(nfft)[:, None] + hop * np.arange(nseg)[None, :]
+    X = np.fft.rfft(x[idx] * window[:, None], n=nfft, axis=0)
+    P = (X.conj() * X).real
+    if nfft % 2 == 0:
+        P[1:-1] *= 2.0
+    else:
+        P[1:] *= 2.0
+    P /= fs
+    P /= (np.abs(window) ** 2).sum()
+    return P, np.fft.rfftfreq(nfft, 1.0 / fs), np.arange(nfft / 2, len(x) - nfft / 2 + 1, hop) / fs
+
+
+def _hz2erbs(hz):
+    return 21.4 * np.log10(1 + hz / 229)
+
+
+def _erbs2hz(erbs):
+    return (np.power(10, erbs / 21.4) - 1) * 229
+
+
+def _is_prime(n):
+    return all(n % i for i in range(2, int(np.sqrt(n)) + 1))          # SWIPE.py:151-158: 1 counts as prime
+
+
+def _candidate_kernel(f, pc):
+    """SWIPE.py:166-184: normalised cosine kernel of one pitch candidate over the ERB frequency grid."""
+    n = np.fix(f[-1] / pc - 0.75)
+    k = np.zeros(len(f))
+    q = f / pc
+    for i in (i for i in range(1, int(n) + 2) if _is_prime(i)):
+        a = np.abs(q - i)
+        peak = a < .25
+        k[peak] = np.cos(2 * np.pi * q[peak])
+        valley = (.25 < a) & (a < .75)
+        k[valley] = np.cos(2 * np.pi * q[valley]) / 2
+    k = k * np.sqrt(1.0 / f)
+    return k / np.linalg.norm(k[k > 0.0])
+
+
+def swipep(x, fs, plim, dt=0.001, dlog2p=1.0 / 96.0, dERBs=0.1):
+    """SWIPE' pitch track (Camacho's sawtooth-waveform-inspired estimator) with the behaviour of the port the
+    reference ships (SWIPE.py:14-132): returns (n,3) rows [t, pitch, strength] every `dt` seconds.  Restated
+    quirks: the last pitch candidate never receives a strength (SWIPE.py:146), a maximum at either end of the
+    candidate range reports the LOWEST candidate (SWIPE.py:115-118), 1 is treated as a prime harmonic."""
+    x = np.asarray(x, float).reshape(-1)
+    t = np.arange(0, len(x) / float(fs), dt)
+    dc, K = 4, 2
+    log2pc = np.arange(np.log2(plim[0]), np.log2(plim[-1]), dlog2p)
+    pc = np.power(2, log2pc)
+    S = np.zeros((len(pc), len(t)))
+    logWs = np.round(np.log2(4 * K * (float(fs) / np.asarray(plim, float))))
+    ws = np.power(2, np.arange(logWs[0], logWs[1] - 1, -1))
+    pO = 4 * K * fs / ws
+    d = 1 + log2pc - np.log2(4 * K * (fs / ws[0]))
+    fERBs = _erbs2hz(np.arange(_hz2erbs(pc[0] / 4), _hz2erbs(fs / 2), dERBs))
+    for i in range(len(ws)):
+        w_i = int(ws[i])
+        dn = round(dc * fs / pO[i])
+        xzp = np.concatenate((np.zeros(int(w_i / 2)), x, np.zeros(int(dn + w_i / 2))))
+        o = max(0, round(w_i - dn))
+        X, f, ti = _psd_spectrogram(xzp, w_i, fs, np.hanning(w_i), int(o))
+        # linear interpolation of every frame's spectrum onto the ERB grid, loudness = sqrt(magnitude)
+        lo = np.clip(np.searchsorted(f, fERBs, side="right") - 1, 0, len(f) - 2)
+        slope = (X[lo + 1, :] - X[lo, :]) / (f[lo + 1] - f[lo])[:, None]
+        Lmat = np.sqrt(np.maximum(0, slope * (fERBs - f[lo])[:, None] + X[lo, :]))
+        if i == len(ws) - 1:
+            j = np.flatnonzero(d - (i + 1) > -1)
+            k = np.flatnonzero(d[j] - (i + 1) < 0)
+        elif i == 0:
+            j = np.flatnonzero(d - (i + 1) < 1)
+            k = np.flatnonzero(d[j] - (i + 1) > 0)
+        else:
+            j = np.flatnonzero(np.abs(d - (i + 1)) < 1)
+            k = np.arange(len(j))
+        nrm = np.sqrt((Lmat * Lmat).sum(axis=0))
+        nrm[nrm == 0] = np.inf
+        Ln = Lmat / nrm[None, :]
+        Si = np.zeros((len(j), Ln.shape[1]))
+        for r, cand in enumerate(pc[j][:-1]):                        # SWIPE.py:146: the last candidate is skipped
+            Si[r, :] = _candidate_kernel(fERBs, cand) @ Ln
+        if Si.shape[1] > 1:
+            tim = np.concatenate(([0.0], ti[:-1]))                   # SWIPE.py:92-97
+            out = np.full((len(j), len(t)), np.nan)
+            inside = (t >= tim[0]) & (t <= tim[-1])
+            hi = np.clip(np.searchsorted(tim, t[inside], side="left"), 1, len(tim) - 1)
+            l0 = hi - 1
+            sl = (Si[:, hi] - Si[:, l0]) / (tim[hi] - tim[l0])[None, :]
+            out[:, inside] = sl * (t[inside] - tim[l0])[None, :] + Si[:, l0]
+            Si = out
+        else:
+            Si = np.full((len(j), len(t)), np.nan)
+        mu = np.ones(len(j))
+        mu[k] = 1 - np.abs(d[j[k]] - (i + 1))
+        S[j, :] = S[j, :] + mu[:, None] * Si
+    # parabolic refinement around the strongest candidate of every frame (SWIPE.py:106-131)
+    p = np.full(len(t), np.nan)
+    s = np.full(len(t), np.nan)
+    for jj in range(len(t)):
+        col = S[:, jj]
+        s[jj] = col.max(0)
+        i = int(np.argmax(col))
+        if i == 0 or i == len(pc) - 1:
+            p[jj] = pc[0]
+        else:
+            I = np.arange(i - 1, i + 2)
+            tc = 1 / pc[I]
+            ntc = ((tc / tc[1]) - 1) * 2 * np.pi
+            c = np.polyfit(ntc, col[I], 2)
+            ftc = 1 / np.power(2, np.arange(np.log2(pc[I[0]]), np.log2(pc[I[2]]), 0.0013021))
+            nftc = ((ftc / tc[1]) - 1) * 2 * np.pi
+            vals = np.polyval(c, nftc)
+            s[jj] = vals.max(0)
+            p[jj] = 2 ** (np.log2(pc[I[0]]) + (int(np.argmax(vals)) - 1) / 768)
+    return np.stack([t, p, s], axis=1)

@@ -326,3 +326,18 @@ def test_api_drop_in_on_sa19_with_supplied_preprocessing(tmp_path):
     nk = int(g["det_nk"][i])
     assert len(d.amplitudes) == nk
     assert abs(float(d.amplitudes[0][0]) - g["det_am"][i, 0]) <= 1e-9 * g["det_am"][i].max()
+
+
+def test_api_drop_in_from_wav_only(tmp_path):
+    """The full drop-in: wav path + gender, nothing supplied; host preprocessing (SWIPE', flags) restated in
+    preprocess.py, hot path on the GPU.  Must give the published SA19 SRER values."""
+    from scipy.io import wavfile
+    from eaqhm_b200.api import eaQHMAnalysisAndSynthesis
+    g, kw = load_golden("sa19")
+    wav = str(tmp_path / "SA19.WAV")
+    wavfile.write(wav, int(g["fs"]), g["pcm"])
+    s_recon, SRER, det, t = eaQHMAnalysisAndSynthesis(wav, "female", printPrompts=False, loadingScreen=False)
+    published = [17.86520945273994, 24.431728752204954, 24.67698055430504, 25.291120491477024, 25.497403658214047,
+                 25.446628776435006]
+    assert len(SRER) == 6 and np.abs(np.array(SRER) - np.array(published)).max() <= 1e-8
+    assert np.abs(s_recon - g["s_recon"]).max() <= TOL_S and len(det) == 4233
