@@ -560,6 +560,160 @@ __global__ void __launch_bounds__(128, 3) k_gram(SolveArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Gram, warp-autonomous variant: the same DMMA tile arithmetic as k_gram, but every warp owns a 16x16 output tile
+// (x 3 weights) end to end: it streams its two 16-column panels through a private double-buffered cp.async ring and
+// never meets a CTA barrier.  Work items (frame, lower-triangular 16x16 tile) are dealt round-robin to all warps of a
+// persistent grid, so ragged frame sizes, partially filled edge tiles and the idle upper warp of diagonal CTA tiles
+// no longer cost barrier stalls (profiles/r01_ncu_summary.md: barrier was the top stall of k_gram).
+// ---------------------------------------------------------------------------------------
+constexpr int kG2K = 16;                 // samples per stage
+constexpr int kG2P = 20;                 // shared-memory pitch in doubles (== 4 mod 16: conflict-free fragments)
+constexpr int kG2Warps = 4;
+constexpr int kG2StageDoubles = 2 /*panel*/ * 2 /*plane*/ * 16 * kG2P;
+constexpr int kGram2Smem = kG2Warps * 2 /*stages*/ * kG2StageDoubles * 8;
+
+__global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int items_per_frame) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * kG2StageDoubles;
+    const long long nitems = (long long)A.nf * items_per_frame;
+    const long long gw = (long long)blockIdx.x * kG2Warps + warp, nw = (long long)gridDim.x * kG2Warps;
+    const size_t plane_stride = (size_t)A.Mxmax * A.Lp;
+
+    for (long long item = gw; item < nitems; item += nw) {
+        const int jl = (int)(item / items_per_frame), t = (int)(item - (long long)jl * items_per_frame);
+        int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) ti--;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        const int tj = t - ti * (ti + 1) / 2;
+        const int Mx = A.Mcols[jl];
+        const int i0 = ti * 16, j0 = tj * 16;
+        if (i0 >= Mx) continue;
+        const int L = A.Lrows[jl], N = (L - 1) / 2;
+        const bool diag = ti == tj;
+        const double* Xf = A.X + (size_t)jl * 2 * A.Mxmax * A.Lp;
+
+        bool act_[2][2];
+#pragma unroll
+        for (int si = 0; si < 2; si++)
+#pragma unroll
+            for (int sj = 0; sj < 2; sj++)
+                act_[si][sj] = (i0 + si * 8 < Mx) && (j0 + sj * 8 < Mx) && (j0 + sj * 8 <= i0 + si * 8);
+
+        double acc[2][2][3][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int d = 0; d < 2; d++) acc[a][b][c][d][0] = acc[a][b][c][d][1] = 0.0;
+
+        // stage loader: panel 0 = tile rows' columns, panel 1 = tile cols' columns (skipped on the diagonal);
+        // per (panel, plane): 16 cols x 16 samples = 128 pieces of 16 B -> 4 per lane
+        auto load_stage = [&](int chunk, int slot) {
+            const int n0 = chunk * kG2K;
+            double* dst0 = ring + (size_t)slot * kG2StageDoubles;
+            const int npanel = diag ? 1 : 2;
+            for (int pnl = 0; pnl < npanel; pnl++) {
+                const int c0 = pnl == 0 ? i0 : j0;
+#pragma unroll
+                for (int plane = 0; plane < 2; plane++) {
+                    double* dst = dst0 + (size_t)(pnl * 2 + plane) * 16 * kG2P;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int idx = lane + e * 32;           // 0..127
+                        const int col = idx >> 3, pc = idx & 7;  // piece pc covers samples n0 + 2pc, +1
+                        const int n = n0 + 2 * pc, gc = c0 + col;
+                        int bytes = 0;
+                        if (gc < Mx) bytes = (n + 1 < L) ? 16 : ((n < L) ? 8 : 0);
+                        const int gcs = gc < Mx ? gc : 0, ns = n < L ? n : 0;
+                        cp_async16(dst + col * kG2P + 2 * pc, Xf + plane * plane_stride + (size_t)gcs * A.Lp + ns, bytes);
+                    }
+                }
+            }
+        };
+
+        const int nst = (L + kG2K - 1) / kG2K;
+        load_stage(0, 0);
+        cp_async_commit();
+        for (int c = 0; c < nst; c++) {
+            if (c + 1 < nst) {
+                load_stage(c + 1, (c + 1) & 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const double* st = ring + (size_t)(c & 1) * kG2StageDoubles;
+            const double* ar_s = st + (0 * 2 + 0) * 16 * kG2P + lr * kG2P + lc;
+            const double* ai_s = st + (0 * 2 + 1) * 16 * kG2P + lr * kG2P + lc;
+            const double* br_s = st + ((diag ? 0 : 1) * 2 + 0) * 16 * kG2P + lr * kG2P + lc;
+            const double* bi_s = st + ((diag ? 0 : 1) * 2 + 1) * 16 * kG2P + lr * kG2P + lc;
+#pragma unroll
+            for (int kk = 0; kk < kG2K; kk += 4) {
+                const double nc = (double)(c * kG2K + kk + lc - N), nc2 = nc * nc;
+                double ar[2], ai[2], nai[2], br[2][3], bi[2][3];
+#pragma unroll
+                for (int si = 0; si < 2; si++) {
+                    ar[si] = ar_s[si * 8 * kG2P + kk];
+                    ai[si] = ai_s[si * 8 * kG2P + kk];
+                    nai[si] = -ai[si];
+                }
+#pragma unroll
+                for (int sj = 0; sj < 2; sj++) {
+                    const double r = br_s[sj * 8 * kG2P + kk], i = bi_s[sj * 8 * kG2P + kk];
+                    br[sj][0] = r; br[sj][1] = r * nc; br[sj][2] = r * nc2;
+                    bi[sj][0] = i; bi[sj][1] = i * nc; bi[sj][2] = i * nc2;
+                }
+#pragma unroll
+                for (int si = 0; si < 2; si++)
+#pragma unroll
+                    for (int sj = 0; sj < 2; sj++)
+                        if (act_[si][sj]) {
+#pragma unroll
+                            for (int wt = 0; wt < 3; wt++) {
+                                dmma884(acc[si][sj][wt][0], ar[si], br[sj][wt]);
+                                dmma884(acc[si][sj][wt][1], ar[si], bi[sj][wt]);
+                                dmma884(acc[si][sj][wt][0], ai[si], bi[sj][wt]);
+                                dmma884(acc[si][sj][wt][1], nai[si], br[sj][wt]);
+                            }
+                        }
+            }
+            __syncwarp();
+        }
+
+        double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+        const int Pp = A.Pp;
+#pragma unroll
+        for (int si = 0; si < 2; si++)
+#pragma unroll
+            for (int sj = 0; sj < 2; sj++) {
+                if (!act_[si][sj]) continue;
+                const int i = i0 + si * 8 + lr;
+                const bool offdiag_sub = (j0 + sj * 8) < (i0 + si * 8);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = j0 + sj * 8 + 2 * lc + e;
+                    if (i >= Mx || j >= Mx) continue;
+                    const double2 a = make_double2(acc[si][sj][0][0][e], acc[si][sj][0][1][e]);
+                    const double2 b = make_double2(acc[si][sj][1][0][e], acc[si][sj][1][1][e]);
+                    const double2 cc = make_double2(acc[si][sj][2][0][e], acc[si][sj][2][1][e]);
+                    if (j <= i) {
+                        RF[(size_t)i * Pp + j] = a;
+                        RF[(size_t)(Mx + i) * Pp + Mx + j] = cc;
+                    }
+                    RF[(size_t)(Mx + i) * Pp + j] = b;
+                    if (offdiag_sub) RF[(size_t)(Mx + j) * Pp + i] = make_double2(b.x, -b.y);
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Adaptation 0: the basis is stationary and harmonic, E2[n,h] = exp(j 2 pi h f0 n / fs) (functions.py:453-454),
 // so every Gram entry depends only on the harmonic-number difference d = h_q - h_p:
 //   sum_n n^e w_n^2 exp(j d theta n),  theta = 2 pi f0 / fs,  e = 0,1,2   (Toeplitz blocks).
@@ -913,9 +1067,28 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
         gram_attr = true;
     }
-    const int Tt = (a.Mxmax + kGT - 1) / kGT;
-    dim3 grid(Tt * (Tt + 1) / 2, a.nf);
-    if (do_gram) LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
+    // experiment knob (tools only): EAQHM_GRAM_VARIANT=1 selects the CTA-tiled kernel
+    static int gram_variant = getenv("EAQHM_GRAM_VARIANT") ? atoi(getenv("EAQHM_GRAM_VARIANT")) : 0;
+    if (do_gram && gram_variant == 1) {
+        const int Tt = (a.Mxmax + kGT - 1) / kGT;
+        dim3 grid(Tt * (Tt + 1) / 2, a.nf);
+        LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
+    } else if (do_gram) {
+        static bool g2_attr = false;
+        static int nsm = 148;
+        if (!g2_attr) {
+            CUDA_TRY(cudaFuncSetAttribute(k_gram_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
+            int dev = 0;
+            CUDA_TRY(cudaGetDevice(&dev));
+            CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+            g2_attr = true;
+        }
+        const int Tt16 = (a.Mxmax + 15) / 16, ipf = Tt16 * (Tt16 + 1) / 2;
+        const long long nitems = (long long)a.nf * ipf;
+        int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
+        if ((long long)blocks * kG2Warps > nitems) blocks = (int)((nitems + kG2Warps - 1) / kG2Warps);
+        LAUNCH(KC_GRAM, st, k_gram_warp<<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
+    }
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
