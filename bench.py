@@ -48,6 +48,19 @@ def shard_inputs(shard_index, seconds):
                 Kmax=int(round(int(cfg["fs"] / 2 - 200) / 90.0) + 10))   # min f0 of the whole hour (functions.py:120)
 
 
+def corpus_inputs(first_index, count, seconds=3.0):
+    """`count` utterances of the config-c3 corpus (10,000 x 3 s at 16 kHz, utterance-sharded) as host arrays."""
+    from eaqhm_b200 import synthetic
+    out = []
+    for i in range(first_index, first_index + count):
+        cfg = synthetic.config_c3(i, duration=seconds)
+        s, f0s = synthetic.make(cfg)
+        n5 = len(np.arange(1, len(s), 80))
+        out.append(dict(s=s, fs=cfg["fs"], f0s=f0s, voiced5=np.ones(n5, bool), frame_step=80, f0min=90.0,
+                        Kmax=int(round(int(cfg["fs"] / 2 - 200) / f0s[:, 1].min()) + 10)))
+    return out
+
+
 def algorithmic_flops(N, M):
     """Structure-aware minimum of one frame solve: three Hermitian half-Grams of the
     M-column basis under weights w^2, n w^2, n^2 w^2 (12 L M^2), rhs (16 L M), complex Cholesky of
@@ -116,6 +129,10 @@ def main():
     ap.add_argument("--shard-seconds", type=float, default=20.0)
     ap.add_argument("--cpu-excerpt-seconds", type=float, default=0.25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the metric's configuration): frame-range shards of the 1-hour signal; "
+                         "c3: a batch of --batch 3-second utterances per GPU per step (utterance sharding)")
+    ap.add_argument("--batch", type=int, default=32)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,12 +187,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    inp = shard_inputs(rank, args.shard_seconds)
-    utt = engine.Utterance(**inp)
+    if args.workload == "c3":
+        inps = corpus_inputs(rank * args.batch, args.batch)
+        utts = [engine.Utterance(**i) for i in inps]
+        inp = inps[0]
+        args.shard_seconds = 3.0 * args.batch
+        config["workload"] = ("c3: batch of %d synthetic 3-second utterances at 16 kHz per GPU per step (utterance-sharded "
+                              "corpus), full eaQHM analysis+synthesis until each utterance's SRER converges" % args.batch)
+        config["parallelism"] = "utterance sharding, %d utterances per GPU per step, no data-path collective" % args.batch
+    else:
+        inp = shard_inputs(rank, args.shard_seconds)
+        utts = [engine.Utterance(**inp)]
     L = _lib.lib()
 
     # ---------------- device-resident arm ----------------------------------------------------
-    eng = engine.Engine([utt])
+    eng = engine.Engine(utts)
     for _ in range(args.warmup):
         res = eng.run_device()
     barrier()
@@ -195,12 +221,12 @@ def main():
     prof = _lib.profile_read()
     ms_dev = ev0.elapsed_time(ev1) / args.steps
     SRER, best_a, frames_solved = res
-    n_adapt = len(SRER[0])
+    n_adapt = int(max(len(x) for x in SRER))
     launches = sum(c for _, c in prof.values()) // args.steps
 
     # ---------------- end-to-end arm (host buffers in, host results out) ----------------------
     def e2e_step():
-        e = engine.Engine([utt])
+        e = engine.Engine(utts)
         r = e.run()
         return e, r
     for _ in range(max(1, min(args.warmup, 2))):
@@ -223,12 +249,10 @@ def main():
     e2e_value = audio / t_e2e
 
     # ---------------- roofline of the dominant kernel ------------------------------------------
-    ft = eng.ft[0]
-    a_idx = np.flatnonzero(ft.analysed)
-    gram_fl, chol_fl, _ = algorithmic_flops(ft.N[a_idx].astype(float), 2.0 * ft.K0[a_idx] + 1)
-    # adaptation 0 uses all K0 harmonics; later adaptations use the accepted subset (<= K0): upper bound on
-    # useful work is n_adapt * sum over frames; report with the actual active counts recorded by the engine
-    useful = eng.useful_flops            # accumulated per step by run_device from the device-side column counts
+    n_frames = int(sum(int(f.analysed.sum()) for f in eng.ft))
+    # algorithmic flops: accumulated on the device by k_active from the actual active-harmonic counts of every
+    # frame solve; adaptation 0 uses Toeplitz tables instead of the Gram and is not counted there
+    useful = eng.useful_flops
     kt = {k: v[0] / args.steps for k, v in prof.items()}
     dom = max(("gram", "chol_solve", "basis"), key=lambda k: kt[k])
     dom_fl = {"gram": useful["gram"], "chol_solve": useful["chol"], "basis": useful["basis"]}[dom]
@@ -243,7 +267,7 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": dict(config, adaptations_run=n_adapt, frames_per_shard=int(len(a_idx)),
+           "data": "synthetic", "config": dict(config, adaptations_run=n_adapt, frames_per_shard=n_frames,
                                                frame_solves_per_step=int(frames_solved),
                                                SRER_dB=[float(x) for x in SRER[0]]),
            "frame_solves_per_s": frames_solved * world / (ms_dev * 1e-3),
