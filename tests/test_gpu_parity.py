@@ -341,3 +341,51 @@ def test_api_drop_in_from_wav_only(tmp_path):
                  25.446628776435006]
     assert len(SRER) == 6 and np.abs(np.array(SRER) - np.array(published)).max() <= 1e-8
     assert np.abs(s_recon - g["s_recon"]).max() <= TOL_S and len(det) == 4233
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ragged_voicing_short_runs_and_isolated_frames_match_oracle(seed):
+    """Voiced-only mode with randomly punched voicing: runs of 1, 2, 3 and more frames per harmonic exercise the
+    isolated-frame impulses (functions.py:350-358), the short-run cubic with knots at samples 0/step (Q4,
+    functions.py:369-371), run boundaries inside analysis windows (gap fill, functions.py:250-278) and the
+    shrinking active set."""
+    from eaqhm_b200 import host, synthetic
+    rng = np.random.default_rng(100 + seed)
+    cfg = synthetic.config_c3(50 + seed, duration=1.2)
+    s, f0s = synthetic.make(cfg)
+    fstep, step = 80, 80          # hop = one 5 ms frame: a burst of b voiced 5 ms frames gives a run of b-1 analysis frames
+    n5 = len(np.arange(1, len(s), fstep))
+    voiced5 = np.ones(n5, bool)
+    pos = 8
+    while pos < n5 - 8:                                   # bursts of 2..6 voiced 5 ms frames, holes of 1..3
+        burst = int(rng.integers(2, 7))
+        pos += burst
+        hole = int(rng.integers(1, 4))
+        voiced5[pos:pos + hole] = False
+        pos += hole
+    det = host.voiced_only_target(s, voiced5, voiced5, fstep)
+    inp = dict(s=s, fs=16000, f0s=f0s, voiced5=voiced5, frame_step=fstep, f0min=90.0,
+               Kmax=host.harmonic_capacity(16000, f0s)[1], det_part=det, step=step, maxAdpt=3, analysisWindow=8)
+    res, ref = run_cuda(inp), run_oracle(inp)
+    assert_close_results(res, ref)
+    v = ref.isVoiced
+    runs = np.diff(np.concatenate(([0], v.astype(int), [0])))
+    lens = np.flatnonzero(runs == -1) - np.flatnonzero(runs == 1)
+    assert lens.min() == 1 and {2, 3} & set(lens.tolist()) and lens.max() >= 4   # isolated, short and long runs
+
+
+@pytest.mark.parametrize("kw", [dict(step=10), dict(step=20, analysisWindow=24), dict(pitchPeriods=4),
+                                dict(partials=20)])
+def test_non_default_parameters_match_oracle(kw):
+    """step / pitchPeriods / analysisWindow / partials (functions.py:35-37) other than the defaults."""
+    from eaqhm_b200 import engine, host, synthetic
+    cfg = synthetic.config_c3(77, duration=0.5)
+    s, f0s = synthetic.make(cfg)
+    n5 = len(np.arange(1, len(s), 80))
+    step, aw, pp = kw.get("step", 15), kw.get("analysisWindow", 32), kw.get("pitchPeriods", 3)
+    Kmax = host.harmonic_capacity(16000, f0s, kw.get("partials", 0))[1]
+    u = engine.Utterance(s=s, fs=16000, f0s=f0s, voiced5=np.ones(n5, bool), frame_step=80, f0min=90.0, Kmax=Kmax)
+    res = engine.Engine([u], step=step, maxAdpt=2, pitchPeriods=pp, analysisWindow=aw).run()[0]
+    ref = O.eaqhm_oracle(s, 16000, f0s, np.ones(n5, bool), 80, 90.0, Kmax, step=step, maxAdpt=2, pitchPeriods=pp,
+                         analysisWindow=aw)
+    assert_close_results(res, ref)
