@@ -259,7 +259,10 @@ def main():
     achieved = dom_fl / (kt[dom] * 1e-3) / 1e12 if kt[dom] > 0 else 0.0
     roofline = {"bound": "tensor", "pipe": "FP64 (DFMA and DMMA share one pipe on sm_100a)", "kernel": dom,
                 "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of k_gram_warp, mean of the four launches captured with
+                # `ncu --set full` on this command's default workload (profiles/r01_ncu_summary_final.md); the algorithmic
+                # bytes of the same launches (basis planes read once + normal matrix written once) are 2.3 GB
+                "traffic": (2.54e9 if (dom == "gram" and args.workload == "c2" and args.shard_seconds == 20.0) else None),
                 "peak_source": "measured FP64 burst (tools/fp64_peak.cu, profiles/r01_fp64_peak.jsonl); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "kernel_ms_per_step": kt, "algorithmic_flops_per_step": useful,
