@@ -51,7 +51,7 @@ __global__ void k_fallback_flags(AnaArgs A) {
         A.fb[g] = any ? 0 : 1;
         if (!any) {
             atomicAdd(&A.status[1], 1);
-            if (A.best_am) A.best_am[g] = kFallbackAm;   // harmonic 0 row: [0][g]
+            if (A.best_am) A.best_am[(int64_t)g * A.t.Kmax] = kFallbackAm;   // harmonic 0 of frame g (snapshot is [G][Kmax])
         }
     }
 }

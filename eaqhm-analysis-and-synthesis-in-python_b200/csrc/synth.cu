@@ -105,10 +105,11 @@ __global__ void k_snapshot_knots(eaqhm_tables t, const uint8_t* improved, eaqhm_
     if (g >= t.G) return;
     const int u = t.utt[g];
     if (!improved[u]) return;
-    const int64_t x = t.pos[g], o = (int64_t)k * t.G + g;
-    best.am[o] = tr.am[(int64_t)k * t.T + x];
-    best.ph[o] = tr.ph[(int64_t)k * t.T + x];
-    best.fm[o] = fm_fin[o];
+    // the snapshot is frame-major [G][Kmax]: it is what the host reads back and slices per utterance
+    const int64_t x = t.pos[g], o = (int64_t)k * t.G + g, ob = (int64_t)g * t.Kmax + k;
+    best.am[ob] = tr.am[(int64_t)k * t.T + x];
+    best.ph[ob] = tr.ph[(int64_t)k * t.T + x];
+    best.fm[ob] = fm_fin[o];
     if (k == 0) best.a0[g] = a0_at(t, a0k, a0mom, u, x - t.ustart[u]);
 }
 

@@ -274,7 +274,7 @@ class Engine:
     def results(self, SRER, best_a, frames_solved=0):
         K, G = self.Kmax, self.G
         s_best = self.s_best.cpu().numpy()
-        b_am, b_ph, b_fm = [x.view(K, G).cpu().numpy() for x in self.best[:3]]
+        b_am, b_ph, b_fm = [x.view(G, K).cpu().numpy() for x in self.best[:3]]      # frame-major snapshot
         b_a0 = self.best[3].cpu().numpy()
         status = self.status.cpu().numpy()
         self.d2h_bytes += s_best.nbytes + 3 * b_am.nbytes + b_a0.nbytes
@@ -286,7 +286,7 @@ class Engine:
             out.append(Result(
                 s_recon=s_best[self.ustart[i]:self.ustart[i] + f.length].copy(), SRER=list(SRER[i]), ti=f.ti0.copy(),
                 isSpeech=f.isSpeech.copy(), isVoiced=f.analysed.copy(), a0=b_a0[sl].copy(),
-                am=b_am[:ku, sl].T.copy(), fm=b_fm[:ku, sl].T.copy(), ph=b_ph[:ku, sl].T.copy(),
+                am=b_am[sl, :ku].copy(), fm=b_fm[sl, :ku].copy(), ph=b_ph[sl, :ku].copy(),
                 n_adapt_best=int(best_a[i]),
                 stats=dict(not_pd_frames=int(status[0]), fallback_frames=int(status[1]),
                            frames_solved=int(frames_solved))))

@@ -112,7 +112,7 @@ int64_t eaqhm_analysis_scratch_bytes(int32_t G, int32_t chunk, int32_t nnz_max, 
  * fill, time-reversed mirror (Q2), adaptive (or harmonic, adapt==0) basis, weighted
  * complex Gram (weight w^2, Q3), Cholesky solve, frequency mismatch, acceptance,
  * knot write.  `knots` must be zero-filled by the caller beforehand.
- * `best_am` (may be NULL): [Kmax][G] snapshot that receives the in-place fallback
+ * `best_am` (may be NULL): [G][Kmax] (frame-major) snapshot that receives the in-place fallback
  * amplitude 10e-4 (the am_fin alias of functions.py:210,383,400).
  * `status` (device, int32[2]): [0] += frames whose matrix was not positive definite,
  * [1] += frames that used the fallback.
@@ -151,7 +151,8 @@ int eaqhm_synthesize(const eaqhm_tables* tab, const eaqhm_tracks* tr, const doub
                      void* work, int64_t work_bytes, void* stream);
 
 /* Snapshot of the best adaptation (functions.py:397-402) for utterances with
- * improved[u] != 0: s_best <- s_hat, and the centre values of a0/am/fm/ph. */
+ * improved[u] != 0: s_best <- s_hat, and the centre values of a0/am/fm/ph.  `best` is
+ * frame-major, [G][Kmax] (+ a0 [G]): the layout the host reads back per utterance. */
 int eaqhm_snapshot(const eaqhm_tables* tab, const uint8_t* improved, const eaqhm_tracks* tr,
                    const eaqhm_knots* knots, const double* fm_fin, const double* a0mom,
                    const double* s_hat, double* s_best, const eaqhm_knots* best, void* stream);
