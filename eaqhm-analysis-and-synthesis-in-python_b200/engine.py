@@ -7,6 +7,7 @@ one concatenated sample axis; utterances adapt in lockstep and drop out of the
 batch when their SRER stops improving (functions.py:394-396).
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -142,6 +143,9 @@ class Engine:
         self.t_f0min = _dev([float(u.f0min) for u in self.utts], np.float64, d)
         self.t_active = torch.ones(U, dtype=torch.uint8, device=d)
         self.alists = [self.gfirst[i] + np.flatnonzero(f.analysed).astype(np.int32) for i, f in enumerate(self.ft)]
+        # cost proxy of a frame solve (~ K^3): launches take the expensive frames first (longest-processing-time order)
+        self.acost = [(f.K0[f.analysed].astype(np.int64) ** 3) for f in self.ft]
+        self.sort_frames = os.environ.get("EAQHM_SORT_FRAMES", "1") != "0"
         self.t_alist = torch.empty(max(1, sum(len(a) for a in self.alists)), dtype=torch.int32, device=d)
         self.s = _dev(cat([np.asarray(u.s, float).reshape(-1) for u in self.utts]), np.float64, d)
         dets = [np.asarray(u.s if u.det_part is None else u.det_part, float).reshape(-1) for u in self.utts]
@@ -202,6 +206,9 @@ class Engine:
         self.h2d_bytes += self.U
         al = [self.alists[i] for i in range(self.U) if act[i]]
         al = np.concatenate(al) if al else np.zeros(0, np.int32)
+        if self.sort_frames and len(al):
+            cost = np.concatenate([self.acost[i] for i in range(self.U) if act[i]])
+            al = al[np.argsort(-cost, kind="stable")]
         if len(al):
             self.t_alist[:len(al)].copy_(torch.from_numpy(al))
             self.h2d_bytes += al.nbytes
