@@ -281,30 +281,51 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 run = __shfl_sync(0xffffffffu, v, 31);
             }
             __syncwarp();
-            // 5. +f column (functions.py:513-519) and the time-reversed -f column (Q2, :284-285):
-            //    cumsum of -fm[::-1] minus its centre value equals S[L-2-n] - S[N-1]
+            // 5. +f column (functions.py:513-519): E1[n] = exp(j 2 pi (S[n] - S[N]) / fs).
+            //    Time-reversed -f column (Q2, :284-285): the running sum of -fm[::-1] minus its centre value equals
+            //    S[L-2-n] - S[N-1], so E1neg[n] = E1[L-2-n] * rho with rho = exp(j 2 pi (S[N] - S[N-1]) / fs): one rotation
+            //    instead of a second sincos per sample.  Pass 1 keeps cos in the (now free) running-sum buffer and parks
+            //    sin in the -f output row; pass 2 walks the index pairs (n, L-2-n), which only touch their own two slots.
             const double Smid = fmw[N], Smid1 = fmw[N - 1], aden = amw[N] + kAmEps;
+            __syncwarp();
             for (int n = lane; n < L; n += 32) {
                 const double nc = (double)(n - N), wn = w[n], v = ws[n];
                 double sn, cs;
-                {
-                    const double t = (kTwoPi * (fmw[n] - Smid)) / fs;
-                    sincos(t, &sn, &cs);
-                    const double r = (kAmEps + amw[n]) / aden;
-                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
-                    pr[n] = xr; pi[n] = xi;
-                    cp.add(xr, xi, nc, wn, v);
-                }
-                {
-                    const int m2 = L - 2 - n;
-                    const double Sm = m2 >= 0 ? fmw[m2] : 0.0;
-                    const double t = (kTwoPi * (Sm - Smid1)) / fs;
-                    sincos(t, &sn, &cs);
-                    const double r = (kAmEps + amw[L - 1 - n]) / aden;
-                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                sincos((kTwoPi * (fmw[n] - Smid)) / fs, &sn, &cs);
+                const double r = (kAmEps + amw[n]) / aden;
+                const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                pr[n] = xr; pi[n] = xi;
+                cp.add(xr, xi, nc, wn, v);
+                fmw[n] = cs; ni[n] = sn;
+            }
+            __syncwarp();
+            double rs, rc;
+            sincos((kTwoPi * (Smid - Smid1)) / fs, &rs, &rc);
+            for (int n = lane; n < N; n += 32) {
+                const int n2 = L - 2 - n;                       // partner index, in [N, 2N-1]
+                const double c1 = fmw[n], s1 = ni[n], c2 = fmw[n2], s2 = ni[n2];
+                {   // -f column at n: E1[n2] * rho, amplitude from sample L-1-n
+                    const double er = c2 * rc - s2 * rs, ei = c2 * rs + s2 * rc;
+                    const double r = (kAmEps + amw[L - 1 - n]) / aden, wn = w[n];
+                    const double xr = (r * er) * wn, xi = (r * ei) * wn;
                     nr[n] = xr; ni[n] = xi;
-                    cn.add(xr, xi, nc, wn, v);
+                    cn.add(xr, xi, (double)(n - N), wn, ws[n]);
                 }
+                {   // -f column at n2: E1[n] * rho, amplitude from sample L-1-n2 = n+1
+                    const double er = c1 * rc - s1 * rs, ei = c1 * rs + s1 * rc;
+                    const double r = (kAmEps + amw[n + 1]) / aden, wn = w[n2];
+                    const double xr = (r * er) * wn, xi = (r * ei) * wn;
+                    nr[n2] = xr; ni[n2] = xi;
+                    cn.add(xr, xi, (double)(n2 - N), wn, ws[n2]);
+                }
+            }
+            if (lane == 0) {   // n = L-1: running sum before the first sample is 0
+                double sn, cs;
+                sincos((kTwoPi * (0.0 - Smid1)) / fs, &sn, &cs);
+                const double r = (kAmEps + amw[0]) / aden, wn = w[L - 1];
+                const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                nr[L - 1] = xr; ni[L - 1] = xi;
+                cn.add(xr, xi, (double)N, wn, ws[L - 1]);
             }
         }
         cp.reduce(); cn.reduce();
