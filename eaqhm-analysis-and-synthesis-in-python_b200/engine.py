@@ -91,6 +91,21 @@ def _workspace(nbytes, device):
     return t
 
 
+_PINNED = {}
+
+
+def _to_host(t, tag):
+    """Device tensor -> numpy through a cached pinned staging buffer (grow-only, one per tag)."""
+    n = t.numel()
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < n or buf.dtype != t.dtype:
+        buf = torch.empty(n, dtype=t.dtype, pin_memory=True)
+        _PINNED[tag] = buf
+    view = buf[:n]
+    view.copy_(t.reshape(-1), non_blocking=True)
+    return view
+
+
 class Engine:
     """Holds the device buffers of one batch and runs the adaptation loop."""
 
@@ -302,10 +317,11 @@ class Engine:
 
     def results(self, SRER, best_a, frames_solved=0):
         K, G = self.Kmax, self.G
-        s_best = self.s_best.cpu().numpy()
-        b_am, b_ph, b_fm = [x.view(G, K).cpu().numpy() for x in self.best[:3]]      # frame-major snapshot
-        b_a0 = self.best[3].cpu().numpy()
-        status = self.status.cpu().numpy()
+        views = [_to_host(self.s_best, "s")] + [_to_host(x, "k%d" % i) for i, x in enumerate(self.best)]
+        status = self.status.cpu().numpy()                                          # synchronises the copies above
+        s_best = views[0].numpy()
+        b_am, b_ph, b_fm = [v.numpy().reshape(G, K) for v in views[1:4]]            # frame-major snapshot
+        b_a0 = views[4].numpy()
         self.d2h_bytes += s_best.nbytes + 3 * b_am.nbytes + b_a0.nbytes
         out = []
         for i, (u, f) in enumerate(zip(self.utts, self.ft)):
