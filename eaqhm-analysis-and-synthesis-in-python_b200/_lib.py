@@ -29,7 +29,8 @@ class Tables(C.Structure):
                 ("K0", C.c_void_p), ("f0", C.c_void_p), ("ustart", C.c_void_p), ("ulen", C.c_void_p),
                 ("gfirst", C.c_void_p), ("gcount", C.c_void_p), ("f0stale", C.c_void_p),
                 ("f0min", C.c_void_p), ("active", C.c_void_p), ("stat_lo", C.c_void_p), ("stat_hi", C.c_void_p),
-                ("alist", C.c_void_p), ("nA", C.c_int32)]
+                ("xoff", C.c_void_p), ("alist", C.c_void_p), ("nA", C.c_int32), ("flist", C.c_void_p),
+                ("nF", C.c_int32)]
 
 
 class Tracks(C.Structure):

@@ -41,8 +41,10 @@ struct AnaArgs {
 // ---------------------------------------------------------------------------------------
 __global__ void k_fallback_flags(AnaArgs A) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= A.t.nA) return;
-    const int g = A.t.alist[w];
+    const int32_t* list = A.t.flist ? A.t.flist : A.t.alist;
+    const int nlist = A.t.flist ? A.t.nF : A.t.nA;
+    if (w >= nlist) return;
+    const int g = list[w];
     const int64_t c = A.t.pos[g];
     bool any = false;
     for (int k = lane; k < A.t.Kmax; k += 32) any |= (A.fm_cur[(int64_t)k * A.t.T + c] != 0.0);
@@ -1171,7 +1173,8 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     CUDA_TRY(cudaMemsetAsync(A.fb, 0, tab->G, st));
     if (adapt > 0) {
         A.j0 = 0; A.nf = tab->nA;
-        LAUNCH(KC_FALLBACK, st, k_fallback_flags<<<(tab->nA * 32 + 255) / 256, 256, 0, st>>>(A));
+        const int nfl = tab->flist ? tab->nF : tab->nA;
+        LAUNCH(KC_FALLBACK, st, k_fallback_flags<<<(nfl * 32 + 255) / 256, 256, 0, st>>>(A));
     }
     for (int j0 = 0; j0 < tab->nA; j0 += chunk) {
         A.j0 = j0;

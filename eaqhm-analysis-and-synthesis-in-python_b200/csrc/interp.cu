@@ -171,16 +171,18 @@ __global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, 
     const int nfwd = next_last ? 0 : (acc(3) ? 2 : 1);
     const bool shortrun = (nback + 2 + nfwd) < 4;
     double LX[4], LY[4];
-    const double xl0 = (double)(x0 - t.ustart[u]);
+    const int64_t xoff = t.xoff[u];                // absolute position of this utterance's first sample
+    const double xl0 = (double)(x0 - t.ustart[u] + xoff);
     if (shortrun) {
-        // knots: extra ones at local samples 0, step (functions.py:369) carrying whatever fm_recon
-        // holds there (the knot values of frames 0 and 1), then the run's own 2 or 3 knots
+        // knots: extra ones at ABSOLUTE samples 0, step (functions.py:369) carrying whatever fm_recon holds there
+        // (the knot values of the signal's frames 0 and 1: zero, they are never analysed, unless this utterance
+        // starts at sample 0 and holds them itself), then the run's own 2 or 3 knots
         const int gs = g - nback;                  // first knot of the run
         const int nrun = nback + 2 + nfwd;
         const int64_t gu = t.gfirst[u];
         int c = 0;
-        for (int e = 0; e < 4 - nrun; e++) { LX[c] = (double)(e * D); LY[c] = fmk[gu + e]; c++; }
-        for (int e = 0; e < nrun; e++) { LX[c] = (double)(t.pos[gs + e] - t.ustart[u]); LY[c] = fmk[gs + e]; c++; }
+        for (int e = 0; e < 4 - nrun; e++) { LX[c] = (double)(e * D); LY[c] = xoff == 0 ? fmk[gu + e] : 0.0; c++; }
+        for (int e = 0; e < nrun; e++) { LX[c] = (double)(t.pos[gs + e] - t.ustart[u] + xoff); LY[c] = fmk[gs + e]; c++; }
     }
     const double f0k = fmk[g], f1k = fmk[g + 1];
     const double m0 = shortrun ? 0.0 : mom[(int64_t)k * G + g], m1 = shortrun ? 0.0 : mom[(int64_t)k * G + g + 1];

@@ -34,6 +34,7 @@ class Utterance:
     stat_range: tuple = None
     group_std_det: float = None
     f0stale: float = None
+    xoff: int = 0                   # position of s[0] inside the signal this utterance was cut from
 
 
 @dataclass
@@ -150,6 +151,7 @@ class Engine:
                                for u, f in zip(self.utts, self.ft)], np.float64, d)
         sr = [(0, f.length) if u.stat_range is None else tuple(u.stat_range) for u, f in zip(self.utts, self.ft)]
         self.stat_n = np.array([hi - lo for lo, hi in sr], np.float64)
+        self.t_xoff = _dev([int(u.xoff) for u in self.utts], np.int64, d)
         self.t_stat_lo = _dev([lo for lo, _ in sr], np.int64, d)
         self.t_stat_hi = _dev([hi for _, hi in sr], np.int64, d)
         # SRER groups: utterances (shards) that share one convergence decision (functions.py:388,394-396)
@@ -201,9 +203,10 @@ class Engine:
         t = self.tab
         t.T, t.maxlen, t.G, t.U, t.Kmax, t.step, t.fs = T, int(lens.max()), G, U, K, self.step, float(fs)
         for name in ("pos", "own", "utt", "N", "K0", "f0", "ustart", "ulen", "gfirst", "gcount", "f0stale",
-                     "f0min", "active", "stat_lo", "stat_hi", "alist"):
+                     "f0min", "active", "stat_lo", "stat_hi", "xoff", "alist"):
             setattr(t, name, getattr(self, "t_" + name).data_ptr())
         t.nA = 0
+        t.flist, t.nF = None, 0
         self.c_tr = _lib.Tracks(*[x.data_ptr() for x in self.tr])
         self.c_kn = _lib.Knots(*[x.data_ptr() for x in self.kn])
         self.c_best = _lib.Knots(*[x.data_ptr() for x in self.best])

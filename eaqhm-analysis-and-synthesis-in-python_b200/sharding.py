@@ -67,7 +67,7 @@ def shard_utterances(s, fs, f0s, voiced5, frame_step, f0min, Kmax, plan, group, 
                              frame_step=frame_step, f0min=f0min, Kmax=Kmax,
                              det_part=None if det_part is None else det[ex_lo:ex_hi], group=group,
                              stat_range=(own_lo - ex_lo, own_hi - ex_lo), group_std_det=std_det,
-                             f0stale=full.f0stale))
+                             f0stale=full.f0stale, xoff=ex_lo))
     return out, full
 
 

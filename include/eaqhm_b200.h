@@ -82,8 +82,14 @@ typedef struct {
     const int64_t* stat_lo;  /* [U] first local sample counted in the SRER statistics          */
     const int64_t* stat_hi;  /* [U] one past the last one (whole utterance: 0, ulen; a frame-   */
                              /*     range shard counts only the samples it owns, not its halo)  */
+    const int64_t* xoff;     /* [U] position of the utterance's first sample inside the signal  */
+                             /*     it was cut from (0 for whole signals): frame-range shards   */
+                             /*     keep the reference's absolute sample coordinates (Q4 knots  */
+                             /*     at samples 0 and step, functions.py:369)                    */
     const int32_t* alist;    /* [nA] analysed frames (global index g), any order               */
     int32_t        nA;
+    const int32_t* flist;    /* [nF] frames whose 140 Hz fallback flag is evaluated (Q6); NULL  */
+    int32_t        nF;       /*      = alist.  A shard lists its halo frames here as well       */
 } eaqhm_tables;
 
 /* Dense per-sample tracks [Kmax][T] (functions.py:159-160,169-171). */
