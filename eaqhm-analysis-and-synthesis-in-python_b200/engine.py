@@ -35,6 +35,10 @@ class Utterance:
     group_std_det: float = None
     f0stale: float = None
     xoff: int = 0                   # position of s[0] inside the signal this utterance was cut from
+    # streamed long signals (longsignal.py): the utterance is an excerpt (owned range + exchanged halo) that analyses
+    # only the frames centred in own_range (local samples); s / det_part may then be device tensors (views of the
+    # resident signal), and the per-frame tables come pre-sliced from the whole signal's (Engine(frame_tables=...))
+    own_range: tuple = None
 
 
 @dataclass
@@ -92,6 +96,23 @@ def _workspace(nbytes, device):
     return t
 
 
+class BufferPool:
+    """Grow-only named device buffers shared by the shard engines of one streamed long signal: a shard engine
+    owns its (small) tables, while tracks / knots / work areas hold data only during that shard's pass."""
+
+    def __init__(self, device):
+        self.device, self.bufs = torch.device(device), {}
+
+    def get(self, name, numel, dtype):
+        t = self.bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            self.bufs.pop(name, None)
+            t = None
+            t = torch.zeros(max(1, numel), dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t[:numel]
+
+
 _PINNED = {}
 
 
@@ -111,7 +132,8 @@ class Engine:
     """Holds the device buffers of one batch and runs the adaptation loop."""
 
     def __init__(self, utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32,
-                 device="cuda", chunk=None, scratch_budget_bytes=None, stats_allgather=None):
+                 device="cuda", chunk=None, scratch_budget_bytes=None, stats_allgather=None, frame_tables=None,
+                 pool=None):
         if not torch.cuda.is_available():
             raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
         self.L = _lib.lib()
@@ -125,8 +147,10 @@ class Engine:
         if any(u.fs != fs for u in self.utts):
             raise ValueError("all utterances of a batch must share the sample rate")
         self.fs, self.step, self.maxAdpt = fs, int(step), int(maxAdpt)
-        self.ft = [FrameTables(len(u.s), fs, u.f0s, u.voiced5, u.frame_step, u.Kmax, step, pitchPeriods,
-                               analysisWindow) for u in self.utts]
+        self.ft = list(frame_tables) if frame_tables is not None else [
+            FrameTables(len(u.s), fs, u.f0s, u.voiced5, u.frame_step, u.Kmax, step, pitchPeriods, analysisWindow)
+            for u in self.utts]
+        self.pool = pool
         self.U = U
         self.Kmax = max(u.Kmax for u in self.utts)
         lens = np.array([f.length for f in self.ft], np.int64)
@@ -159,31 +183,58 @@ class Engine:
         self.stats_allgather = stats_allgather
         self.t_f0min = _dev([float(u.f0min) for u in self.utts], np.float64, d)
         self.t_active = torch.ones(U, dtype=torch.uint8, device=d)
-        self.alists = [self.gfirst[i] + np.flatnonzero(f.analysed).astype(np.int32) for i, f in enumerate(self.ft)]
+        # frames each utterance analyses: all gated frames (functions.py:180-181), or for an excerpt of a streamed
+        # long signal those centred in the range it owns; the 140 Hz fallback flags (Q6) are then also evaluated on
+        # the neighbours' frames whose centre an owned window can reach
+        def owned(u, f, margin):
+            if u.own_range is None:
+                return f.analysed
+            return f.analysed & (f.ti0 >= u.own_range[0] - margin) & (f.ti0 < u.own_range[1] + margin)
+        self.N_max = int(max(1, max(int(f.N.max()) for f in self.ft)))
+        sel = [owned(u, f, 0) for u, f in zip(self.utts, self.ft)]
+        self.alists = [self.gfirst[i] + np.flatnonzero(m).astype(np.int32) for i, m in enumerate(sel)]
+        self.flists = None
+        if any(u.own_range is not None for u in self.utts):
+            self.flists = [self.gfirst[i] + np.flatnonzero(owned(u, f, self.N_max)).astype(np.int32)
+                           for i, (u, f) in enumerate(zip(self.utts, self.ft))]
+            self.t_flist = torch.empty(max(1, sum(len(a) for a in self.flists)), dtype=torch.int32, device=d)
         # cost proxy of a frame solve (~ K^3): launches take the expensive frames first (longest-processing-time order)
-        self.acost = [(f.K0[f.analysed].astype(np.int64) ** 3) for f in self.ft]
+        self.acost = [(f.K0[m].astype(np.int64) ** 3) for f, m in zip(self.ft, sel)]
         self.sort_frames = os.environ.get("EAQHM_SORT_FRAMES", "1") != "0"
         self.t_alist = torch.empty(max(1, sum(len(a) for a in self.alists)), dtype=torch.int32, device=d)
-        self.s = _dev(cat([np.asarray(u.s, float).reshape(-1) for u in self.utts]), np.float64, d)
-        dets = [np.asarray(u.s if u.det_part is None else u.det_part, float).reshape(-1) for u in self.utts]
-        self.det = _dev(cat(dets), np.float64, d)
-        self.std_det = np.array([np.std(x) if u.group_std_det is None else float(u.group_std_det)
-                                 for u, x in zip(self.utts, dets)])          # functions.py:161
+        if all(torch.is_tensor(u.s) for u in self.utts) and U == 1:
+            # excerpt of a signal that is already resident: views, no copies
+            u = self.utts[0]
+            self.s = u.s
+            self.det = u.s if u.det_part is None else u.det_part
+            assert self.s.is_cuda and self.s.dtype == torch.float64 and self.s.is_contiguous()
+            if u.group_std_det is None:
+                raise ValueError("a device-resident excerpt needs the whole signal's target std (group_std_det)")
+            self.std_det = np.array([float(u.group_std_det)])
+        else:
+            self.s = _dev(cat([np.asarray(u.s, float).reshape(-1) for u in self.utts]), np.float64, d)
+            dets = [np.asarray(u.s if u.det_part is None else u.det_part, float).reshape(-1) for u in self.utts]
+            self.det = _dev(cat(dets), np.float64, d)
+            self.std_det = np.array([np.std(x) if u.group_std_det is None else float(u.group_std_det)
+                                     for u, x in zip(self.utts, dets)])          # functions.py:161
         self.nnz_max = int(max(1, max(int(f.K0.max()) for f in self.ft)))
-        self.N_max = int(max(1, max(int(f.N.max()) for f in self.ft)))
         K, T, G = self.Kmax, self.T, self.G
-        f64 = dict(dtype=torch.float64, device=d)
-        self.tr = [torch.zeros(K * T, **f64) for _ in range(3)]              # am, ph, fmc  [Kmax][T]
-        self.kn = [torch.zeros(K * G, **f64) for _ in range(3)] + [torch.zeros(G, **f64)]    # am, ph, fm, a0
-        self.best = [torch.zeros(K * G, **f64) for _ in range(3)] + [torch.zeros(G, **f64)]
-        self.fm_fin = torch.zeros(K * G, **f64)
-        self.a0mom = torch.zeros(G, **f64)
-        self.s_hat = torch.zeros(T, **f64)
-        self.s_best = torch.zeros(T, **f64)
-        self.stat = torch.zeros(2 * U, **f64)
-        self.improved = torch.zeros(U, dtype=torch.uint8, device=d)
-        self.status = torch.zeros(2, dtype=torch.int32, device=d)
-        self.flops = torch.zeros(3, **f64)
+
+        def buf(name, numel, dtype=torch.float64):
+            if self.pool is not None:
+                return self.pool.get(name, numel, dtype)
+            return torch.zeros(numel, dtype=dtype, device=d)
+        self.tr = [buf("tr%d" % i, K * T) for i in range(3)]                 # am, ph, fmc  [Kmax][T]
+        self.kn = [buf("kn%d" % i, K * G) for i in range(3)] + [buf("kn3", G)]               # am, ph, fm, a0
+        self.best = [buf("best%d" % i, K * G) for i in range(3)] + [buf("best3", G)]
+        self.fm_fin = buf("fm_fin", K * G)
+        self.a0mom = buf("a0mom", G)
+        self.s_hat = buf("s_hat", T)
+        self.s_best = buf("s_best", T)
+        self.stat = buf("stat", 2 * U)
+        self.improved = buf("improved", U, torch.uint8)
+        self.status = buf("status", 2, torch.int32)
+        self.flops = buf("flops", 3)
         nA = int(self.t_alist.numel())
         if chunk is None:
             if scratch_budget_bytes is None:
@@ -197,8 +248,8 @@ class Engine:
         nb = self.L.eaqhm_analysis_scratch_bytes(G, self.chunk, self.nnz_max, self.N_max)
         self.scratch = _workspace(nb, d)
         self.scratch_bytes = int(nb)
-        self.iwork = torch.empty(self.L.eaqhm_interp_work_bytes(G, K), dtype=torch.uint8, device=d)
-        self.swork = torch.empty(self.L.eaqhm_synth_work_bytes(int(lens.max()), U), dtype=torch.uint8, device=d)
+        self.iwork = buf("iwork", self.L.eaqhm_interp_work_bytes(G, K), torch.uint8)
+        self.swork = buf("swork", self.L.eaqhm_synth_work_bytes(int(lens.max()), U), torch.uint8)
         self.tab = _lib.Tables()
         t = self.tab
         t.T, t.maxlen, t.G, t.U, t.Kmax, t.step, t.fs = T, int(lens.max()), G, U, K, self.step, float(fs)
@@ -207,6 +258,7 @@ class Engine:
             setattr(t, name, getattr(self, "t_" + name).data_ptr())
         t.nA = 0
         t.flist, t.nF = None, 0
+        self.best_am_ptr = None         # default: this engine's own snapshot (Q10); a streamed signal points it at its store
         self.c_tr = _lib.Tracks(*[x.data_ptr() for x in self.tr])
         self.c_kn = _lib.Knots(*[x.data_ptr() for x in self.kn])
         self.c_best = _lib.Knots(*[x.data_ptr() for x in self.best])
@@ -231,6 +283,13 @@ class Engine:
             self.t_alist[:len(al)].copy_(torch.from_numpy(al))
             self.h2d_bytes += al.nbytes
         self.tab.nA = int(len(al))
+        if self.flists is not None:
+            fl = [self.flists[i] for i in range(self.U) if act[i]]
+            fl = np.concatenate(fl) if fl else np.zeros(0, np.int32)
+            if len(fl):
+                self.t_flist[:len(fl)].copy_(torch.from_numpy(fl))
+                self.h2d_bytes += fl.nbytes
+            self.tab.flist, self.tab.nF = self.t_flist.data_ptr(), int(len(fl))
         return int(len(al))
 
     def analysis(self, a):
@@ -238,7 +297,8 @@ class Engine:
         for x in self.kn:
             x.zero_()
         _lib.check(self.L.eaqhm_analysis(C.byref(self.tab), self.s.data_ptr(), C.byref(self.c_tr), C.byref(self.c_kn),
-                                         self.best[0].data_ptr(), a, self.nnz_max, self.N_max, self.chunk,
+                                         self.best_am_ptr or self.best[0].data_ptr(), a, self.nnz_max, self.N_max,
+                                         self.chunk,
                                          self.scratch.data_ptr(), self.scratch_bytes, self.status.data_ptr(),
                                          self.flops.data_ptr(), self._stream()))
 

@@ -104,3 +104,26 @@ class FrameTables:
         self.f0stale = float(self.f0[idx[-1]]) if len(idx) else 0.0       # quirk Q1
         self.own = np.full(self.No_ti, step, np.int32)
         self.own[-1] = length - self.ti0[-1]
+
+    def excerpt(self, lo, hi):
+        """Tables of the sample range [lo, hi) of this signal (lo a multiple of step), with the SAME per-frame
+        values as the whole signal's (f0, K, N, flags are sliced, not recomputed, so a frame-range shard analyses
+        bit-identical frames); centres become excerpt-local.  Frames whose window leaves the excerpt keep their
+        flags: the caller restricts the analysed list to the frames it owns (longsignal.py)."""
+        if lo % self.step or not (0 <= lo < hi <= self.length):
+            raise ValueError("excerpt must start on the frame grid and lie inside the signal")
+        e = object.__new__(FrameTables)
+        e.length, e.step = int(hi - lo), self.step
+        g0 = lo // self.step
+        n = len(np.arange(1, e.length, self.step))
+        if n < 4 or g0 + n > self.No_ti:
+            raise ValueError("excerpt too short or off the frame grid")
+        e.No_ti, e.g0 = n, int(g0)
+        sl = slice(g0, g0 + n)
+        e.isSpeech, e.analysed = self.isSpeech[sl].copy(), self.analysed[sl].copy()
+        e.f0, e.K0, e.N = self.f0[sl].copy(), self.K0[sl].copy(), self.N[sl].copy()
+        e.ti0 = self.ti0[sl] - lo
+        e.f0stale = self.f0stale
+        e.own = np.full(n, self.step, np.int32)
+        e.own[-1] = e.length - e.ti0[-1]
+        return e

@@ -1,0 +1,287 @@
+"""One long signal as contiguous frame ranges (BASELINE config c2): streamed over the shards of a
+GPU and split over GPUs with a per-adaptation halo exchange of per-frame parameters.
+
+What persists between adaptations is only the per-frame parameter store (amplitude, phase, frequency of every
+harmonic and the DC value at every frame centre: 3*Kmax+1 doubles per frame, frame-major); the dense per-sample
+tracks of the reference (functions.py:159-160,169-171; length x Kmax x 3 doubles, 134 GB for the 1-hour signal) are
+rebuilt shard by shard from that store whenever a stage needs them.  One adaptation a (functions.py:163-402) is
+
+  pass 1, every shard:  tracks(a-1) <- interpolate(store_cur over the shard's excerpt)          [a > 0]
+                        analysis(a) of the frames the shard owns  -> rows of store_new           (functions.py:176-329)
+  exchange:             the first / last `halo` owned rows of store_new go to the previous / next rank, which
+                        keeps them as its halo rows (torch.distributed send/recv: NCCL over NVLink on GPUs)
+  pass 2, every shard:  tracks(a) <- interpolate(store_new over the excerpt)                     (functions.py:337-383)
+                        s_hat, residual statistics over the owned samples                        (functions.py:385-388)
+                        centre values of adaptation a -> rows of the candidate store             (functions.py:397-402)
+  decision:             (n, mean, M2) of all shards of all ranks are all-gathered and merged -> the signal's SRER;
+                        candidate becomes best unless SRER[a] <= SRER[a-1], which stops every rank (functions.py:394-396)
+
+An excerpt is the owned range plus `halo` samples on each side: halo >= N_max + 34*step, because an owned frame's
+window reaches N_max samples into the neighbour (functions.py:193,196) and the cubic splines couple ~32 knots
+(0.268^32 influence).  The halo does not depend on the number of adaptations and no frame is analysed
+twice.  With one shard per rank the tracks built in pass 2 are reused by pass 1 of the next adaptation.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import BufferPool, Engine, Result, Utterance, _to_host, merge_stats
+from .host import FrameTables
+from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks, make_allgather
+
+NROW = 4      # stores: am, ph, fm [rows][Kmax] + a0 [rows]
+
+
+def exchange_halo_samples(N_max, step, analysisWindow, align):
+    """Halo of an excerpt: window reach + spline coupling, and wide enough that the excerpt-edge frames the local
+    gating would drop (functions.py:180) are never inside an owned window."""
+    h = N_max + (SPLINE_HALO_KNOTS + 2) * step
+    return int(-(-h // align) * align)
+
+
+def plan_ranges(length, shard_samples, halo, align, world):
+    """Per rank: list of (own_lo, own_hi, ex_lo, ex_hi).  Owned ranges tile [0, length), are multiples of `align`
+    (a multiple of step, so excerpts start on the frame grid) and every rank gets a contiguous block of them."""
+    shard_samples = max(align, int(shard_samples) // align * align)
+    own, lo = [], 0
+    while lo < length:
+        hi = min(length, lo + shard_samples)
+        if length - hi < shard_samples // 2:
+            hi = length
+        own.append((lo, hi))
+        lo = hi
+    if len(own) < world:
+        raise ValueError("fewer shards (%d) than ranks (%d): lower shard_seconds" % (len(own), world))
+    out = []
+    for first, last in contiguous_blocks(len(own), world):
+        out.append([(a, b, max(0, a - halo), min(length, b + halo)) for a, b in own[first:last]])
+    return out
+
+
+def exchange_halo_rows(store, own_rows, halo_rows, rank, world, dist):
+    """The per-adaptation neighbour exchange: `store` is a list of tensors whose dim 0 indexes this rank's frames
+    [first owned - halo_rows, last owned + halo_rows) (clipped at the signal ends); rows [own_rows[0], own_rows[1])
+    are owned.  The first halo_rows owned rows go to rank-1 and land in its right halo; the last ones go to rank+1.
+    Works on whatever device the store lives on (NCCL for CUDA tensors, gloo for the CPU test)."""
+    if dist is None or world == 1:
+        return 0
+    o0, o1 = own_rows
+    H = halo_rows
+    ops, recvs, sent = [], [], 0
+    width = sum(int(np.prod(t.shape[1:])) for t in store)
+
+    def pack(r0, r1):
+        return torch.cat([t[r0:r1].reshape(r1 - r0, -1) for t in store], dim=1).contiguous()
+
+    def unpack(buf, r0):
+        c = 0
+        for t in store:
+            w = int(np.prod(t.shape[1:]))
+            t[r0:r0 + buf.shape[0]] = buf[:, c:c + w].reshape((buf.shape[0],) + tuple(t.shape[1:]))
+            c += w
+    if rank > 0:
+        out = pack(o0, o0 + H)
+        inc = torch.empty((H, width), dtype=out.dtype, device=out.device)
+        ops += [dist.P2POp(dist.isend, out, rank - 1), dist.P2POp(dist.irecv, inc, rank - 1)]
+        recvs.append((inc, o0 - H))
+        sent += out.numel() * out.element_size()
+    if rank < world - 1:
+        out = pack(o1 - H, o1)
+        inc = torch.empty((H, width), dtype=out.dtype, device=out.device)
+        ops += [dist.P2POp(dist.isend, out, rank + 1), dist.P2POp(dist.irecv, inc, rank + 1)]
+        recvs.append((inc, o1))
+        sent += out.numel() * out.element_size()
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for inc, r0 in recvs:
+        unpack(inc, r0)
+    return sent
+
+
+class LongSignalEngine:
+    """eaQHM adaptation loop of one long signal on this rank's contiguous frame range (see the module docstring)."""
+
+    def __init__(self, s, fs, f0s, voiced5, frame_step, f0min, Kmax, shard_seconds=20.0, det_part=None, step=15,
+                 maxAdpt=10, pitchPeriods=3, analysisWindow=32, rank=0, world=1, dist=None, device="cuda",
+                 full_tables=None, **engine_kw):
+        if not torch.cuda.is_available():
+            raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
+        self.device = torch.device(device)
+        self.rank, self.world, self.dist = int(rank), int(world), dist
+        self.fs, self.step, self.maxAdpt, self.Kmax = fs, int(step), int(maxAdpt), int(Kmax)
+        s = np.asarray(s, float).reshape(-1)
+        det = s if det_part is None else np.asarray(det_part, float).reshape(-1)
+        self.full = full_tables if full_tables is not None else FrameTables(
+            len(s), fs, f0s, voiced5, frame_step, Kmax, step, pitchPeriods, analysisWindow)
+        full = self.full
+        align = int(np.lcm(self.step, int(frame_step)))
+        self.halo = exchange_halo_samples(int(full.N.max()), self.step, analysisWindow, align)
+        self.H = self.halo // self.step
+        self.plan_all = plan_ranges(full.length, int(shard_seconds * fs), self.halo, align, self.world)
+        self.plan = self.plan_all[self.rank]
+        self.R_lo, self.R_hi = self.plan[0][0], self.plan[-1][1]
+        cdiv = lambda a, b: -(-a // b)
+        self.F_lo, self.F_hi = cdiv(self.R_lo, self.step), min(full.No_ti, cdiv(self.R_hi, self.step))
+        if self.world > 1 and self.F_hi - self.F_lo < self.H:
+            raise ValueError("a rank must own at least the halo (%d frames)" % self.H)
+        self.S_lo, self.S_hi = max(0, self.F_lo - self.H), min(full.No_ti, self.F_hi + self.H)
+        rows = self.S_hi - self.S_lo
+        d, K = self.device, self.Kmax
+        # resident signal of this rank: owned range + halo
+        self.X_lo, self.X_hi = self.plan[0][2], self.plan[-1][3]
+        self.h2d_bytes = 2 * (self.X_hi - self.X_lo) * 8
+        self.d2h_bytes = 0
+        self.s_dev = torch.from_numpy(np.ascontiguousarray(s[self.X_lo:self.X_hi])).to(d)
+        self.det_dev = self.s_dev if det_part is None else torch.from_numpy(
+            np.ascontiguousarray(det[self.X_lo:self.X_hi])).to(d)
+        self.std_det = float(np.std(det))                                    # functions.py:161
+        f64 = dict(dtype=torch.float64, device=d)
+
+        def store():
+            return [torch.zeros((rows, K), **f64) for _ in range(3)] + [torch.zeros(rows, **f64)]
+        self.cur, self.new, self.cand, self.best = store(), store(), store(), store()
+        self.s_hat = torch.zeros(self.R_hi - self.R_lo, **f64)
+        self.s_best = torch.zeros(self.R_hi - self.R_lo, **f64)
+        self.pool = BufferPool(d)
+        self.shards = []
+        for own_lo, own_hi, ex_lo, ex_hi in self.plan:
+            ft = full.excerpt(ex_lo, ex_hi)
+            u = Utterance(s=self.s_dev[ex_lo - self.X_lo:ex_hi - self.X_lo], fs=fs, f0s=None, voiced5=None,
+                          frame_step=frame_step, f0min=f0min, Kmax=K,
+                          det_part=None if det_part is None else self.det_dev[ex_lo - self.X_lo:ex_hi - self.X_lo],
+                          stat_range=(own_lo - ex_lo, own_hi - ex_lo), group_std_det=self.std_det,
+                          f0stale=full.f0stale, xoff=ex_lo, own_range=(own_lo - ex_lo, own_hi - ex_lo))
+            e = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow,
+                       device=d, frame_tables=[ft], pool=self.pool, **engine_kw)
+            e.set_active([True])
+            g_lo, g_hi = cdiv(own_lo, self.step), min(full.No_ti, cdiv(own_hi, self.step))
+            self.shards.append(dict(eng=e, ft=ft, own=(own_lo, own_hi), ex=(ex_lo, ex_hi),
+                                    r0=ft.g0 - self.S_lo,                     # store row of the excerpt's first frame
+                                    l0=g_lo - ft.g0, l1=g_hi - ft.g0,         # owned frames, excerpt-local
+                                    n_stat=float(own_hi - own_lo)))
+            self.h2d_bytes += e.h2d_bytes
+        self.tracks_hold = None          # (shard index, adaptation) whose tracks the pool currently holds
+        self.exchanged_bytes = 0
+        self.frames_owned = int(sum(len(sh["eng"].alists[0]) for sh in self.shards))
+
+    # --------------------------------------------------------------------------------------------------
+    def _load_knots(self, sh, store):
+        """Excerpt rows of a frame-major store -> the engine's harmonic-major knot buffers [Kmax][G]."""
+        e, r0 = sh["eng"], sh["r0"]
+        G, K = e.G, self.Kmax
+        for i in range(3):
+            e.kn[i].view(K, G).copy_(store[i][r0:r0 + G].t())
+        e.kn[3].copy_(store[3][r0:r0 + G])
+
+    def _store_owned(self, sh, store):
+        """Owned frames of the engine's knot buffers -> rows of a store."""
+        e, r0, l0, l1 = sh["eng"], sh["r0"], sh["l0"], sh["l1"]
+        G, K = e.G, self.Kmax
+        for i in range(3):
+            store[i][r0 + l0:r0 + l1].copy_(e.kn[i].view(K, G)[:, l0:l1].t())
+        store[3][r0 + l0:r0 + l1].copy_(e.kn[3][l0:l1])
+
+    def _best_am_ptr(self, sh):
+        # Q10 (functions.py:210,383,400): the fallback's in-place amplitude lands in the rows of the best store
+        return self.best[0].data_ptr() + sh["r0"] * self.Kmax * 8
+
+    def run_device(self, on_adaptation=None):
+        """Adaptation loop; results stay on the device.  Returns (SRER list, best adaptation, frame solves)."""
+        SRER, best_a, solves = [], 0, 0
+        ones = np.ones(1, bool)
+        nsh = len(self.shards)
+        stat_dev = torch.zeros((nsh, 2), dtype=torch.float64, device=self.device)
+        self.pool.get("status", 2, torch.int32).zero_()
+        self.pool.get("flops", 3, torch.float64).zero_()
+        self.exchanged_bytes = 0
+        self.tracks_hold = None
+        for a in range(self.maxAdpt + 1):
+            # ---- pass 1: analysis of adaptation a on the tracks of adaptation a-1 -----------------------------
+            order = list(range(nsh))
+            if self.tracks_hold is not None and self.tracks_hold[1] == a - 1:
+                j = self.tracks_hold[0]                  # start with the shard whose tracks are still resident
+                order = [j] + [i for i in order if i != j]
+            for j in order:
+                sh = self.shards[j]
+                e = sh["eng"]
+                if a > 0 and self.tracks_hold != (j, a - 1):
+                    self._load_knots(sh, self.cur)
+                    e.interpolate()
+                e.best_am_ptr = self._best_am_ptr(sh)
+                e.analysis(a)
+                self.tracks_hold = None
+                self._store_owned(sh, self.new)
+                solves += e.tab.nA
+            # ---- neighbour exchange of the new per-frame parameters --------------------------------------------
+            self.exchanged_bytes += exchange_halo_rows(self.new, (self.F_lo - self.S_lo, self.F_hi - self.S_lo),
+                                                       self.H, self.rank, self.world, self.dist)
+            # ---- pass 2: tracks of adaptation a, resynthesis, statistics, candidate snapshot --------------------
+            for j in range(nsh):
+                sh = self.shards[j]
+                e = sh["eng"]
+                self._load_knots(sh, self.new)
+                e.interpolate()
+                self.tracks_hold = (j, a)
+                stat_dev[j].copy_(e.synthesize())
+                e.snapshot(ones)
+                own_lo, own_hi = sh["own"]
+                ex_lo = sh["ex"][0]
+                self.s_hat[own_lo - self.R_lo:own_hi - self.R_lo].copy_(e.s_hat[own_lo - ex_lo:own_hi - ex_lo])
+                G, K, r0, l0, l1 = e.G, self.Kmax, sh["r0"], sh["l0"], sh["l1"]
+                for i in range(3):
+                    self.cand[i][r0 + l0:r0 + l1].copy_(e.best[i].view(G, K)[l0:l1])
+                self.cand[3][r0 + l0:r0 + l1].copy_(e.best[3][l0:l1])
+            stat = stat_dev.cpu().numpy()                                      # the one host sync per adaptation
+            self.d2h_bytes += stat.nbytes
+            rows = [("long", self.shards[j]["n_stat"], stat[j, 0], stat[j, 1]) for j in range(nsh)]
+            if self.dist is not None and self.world > 1:
+                rows = make_allgather(self.dist)(rows)
+            n, _, m2 = merge_stats(rows)["long"]
+            with np.errstate(all="ignore"):
+                srer = 20 * np.log10(self.std_det / np.sqrt(m2 / n))           # functions.py:388
+            SRER.append(srer)
+            if on_adaptation is not None:
+                on_adaptation(a, SRER)
+            if a != 0 and srer <= SRER[a - 1]:                                 # functions.py:394-396
+                break
+            self.best, self.cand = self.cand, self.best                       # functions.py:397-402
+            self.s_best, self.s_hat = self.s_hat, self.s_best
+            self.cur, self.new = self.new, self.cur
+            best_a = a
+        fl = self.pool.get("flops", 3, torch.float64).cpu().numpy()
+        self.useful_flops = dict(gram=float(fl[0]), chol=float(fl[1]), basis=float(fl[2]))
+        return SRER, best_a, solves
+
+    def results(self, SRER, best_a, solves=0):
+        """Owned part of the result as host arrays inside a full-length Result (zeros outside this rank's range)."""
+        full, K = self.full, self.Kmax
+        o0, o1 = self.F_lo - self.S_lo, self.F_hi - self.S_lo
+        views = [_to_host(self.s_best, "ls")] + [_to_host(x[o0:o1], "lk%d" % i) for i, x in enumerate(self.best)]
+        status = self.pool.get("status", 2, torch.int32).cpu().numpy()
+        n = self.F_hi - self.F_lo
+        s_recon = np.zeros(full.length)
+        s_recon[self.R_lo:self.R_hi] = views[0].numpy()
+        am, fm, ph = (np.zeros((full.No_ti, K)) for _ in range(3))
+        a0 = np.zeros(full.No_ti)
+        am[self.F_lo:self.F_hi] = views[1].numpy().reshape(n, K)
+        ph[self.F_lo:self.F_hi] = views[2].numpy().reshape(n, K)
+        fm[self.F_lo:self.F_hi] = views[3].numpy().reshape(n, K)
+        a0[self.F_lo:self.F_hi] = views[4].numpy()
+        self.d2h_bytes += (self.R_hi - self.R_lo) * 8 + n * (3 * K + 1) * 8
+        return Result(s_recon=s_recon, SRER=list(SRER), ti=full.ti0.copy(), isSpeech=full.isSpeech.copy(),
+                      isVoiced=full.analysed.copy(), a0=a0, am=am, fm=fm, ph=ph, n_adapt_best=int(best_a),
+                      stats=dict(shards=len(self.shards), frames_solved=int(solves), not_pd_frames=int(status[0]),
+                                 fallback_flags=int(status[1]), exchanged_bytes=int(self.exchanged_bytes),
+                                 owned_samples=(self.R_lo, self.R_hi), owned_frames=(self.F_lo, self.F_hi)))
+
+    def run(self, on_adaptation=None):
+        return self.results(*self.run_device(on_adaptation))
+
+
+def analyze_long_signal(s, fs, f0s, voiced5, frame_step, f0min, Kmax, shard_seconds=20.0, det_part=None, step=15,
+                        maxAdpt=10, pitchPeriods=3, analysisWindow=32, rank=0, world=1, dist=None, **engine_kw):
+    """Frame-range sharded analysis of one long signal.  Returns (Result holding this rank's owned range inside
+    full-length arrays, plan of all ranks, this rank's owned sample range)."""
+    eng = LongSignalEngine(s, fs, f0s, voiced5, frame_step, f0min, Kmax, shard_seconds, det_part, step, maxAdpt,
+                           pitchPeriods, analysisWindow, rank, world, dist, **engine_kw)
+    return eng.run(), eng.plan_all, (eng.R_lo, eng.R_hi)

@@ -1,12 +1,13 @@
 """CPU: the host side of the multi-GPU partitioning, including a world_size-2 gloo run of the
-statistics exchange that lets every shard take the same convergence decision."""
+per-adaptation halo exchange of per-frame parameters and of the statistics exchange that lets every rank take the
+same convergence decision."""
 import os
 import socket
 
 import numpy as np
 import pytest
 
-from eaqhm_b200 import engine, sharding
+from eaqhm_b200 import engine, longsignal, sharding
 
 
 def test_partitions_cover_everything_once():
@@ -18,40 +19,45 @@ def test_partitions_cover_everything_once():
         assert max(b - a for a, b in cb) - min(b - a for a, b in cb) <= 1
 
 
-def test_shard_plan_alignment_and_cover():
+def test_range_plan_alignment_and_cover():
     length, align = 16000 * 7 + 123, 240
-    halo = sharding.halo_samples(267, 15, 10, 32, align)
-    assert halo % align == 0 and halo >= 480 + 11 * (267 + 480)
-    plan = sharding.plan_shards(length, 16000 * 2, halo, align)
-    assert plan[0][0] == 0 and plan[-1][1] == length
-    for (lo, hi, elo, ehi), nxt in zip(plan, plan[1:] + [None]):
-        assert lo % align == 0 and elo % align == 0 and elo <= lo < hi <= ehi <= length
-        assert elo == max(0, lo - halo) and ehi == min(length, hi + halo)
-        if nxt is not None:
-            assert hi == nxt[0]
+    halo = longsignal.exchange_halo_samples(267, 15, 32, align)
+    # window reach + 32 spline knots, independent of the number of adaptations; the excerpt-edge frames that the
+    # reference's gating would drop (analysisWindow*step samples, functions.py:180) stay outside every owned window
+    assert halo % align == 0 and halo >= 267 + 32 * 15 and halo - 267 >= 32 * 15
+    for world in (1, 2, 3):
+        plans = longsignal.plan_ranges(length, 16000 * 2, halo, align, world)
+        flat = [p for r in plans for p in r]
+        assert len(plans) == world and flat[0][0] == 0 and flat[-1][1] == length
+        for (lo, hi, elo, ehi), nxt in zip(flat, flat[1:] + [None]):
+            assert lo % align == 0 and elo % 15 == 0 and elo <= lo < hi <= ehi <= length
+            assert elo == max(0, lo - halo) and ehi == min(length, hi + halo)
+            if nxt is not None:
+                assert hi == nxt[0]
+    with pytest.raises(ValueError):
+        longsignal.plan_ranges(length, 16000 * 4, halo, align, 8)
 
 
-def test_shard_utterances_share_grid_group_and_stale_f0():
+def test_excerpt_tables_are_slices_of_the_signal_tables():
     fs, step, fstep = 16000, 15, 80
-    length = fs * 3
+    length = fs * 3 + 77
     t5 = np.arange(0, length - 1, fstep) / fs
     f0s = np.stack([t5, 150 + 20 * np.sin(2 * np.pi * t5), np.ones_like(t5)], axis=1)
-    s = np.random.default_rng(0).standard_normal(length) * 0.1
     voiced5 = np.ones(len(np.arange(1, length, fstep)), bool)
-    plan = sharding.plan_shards(length, fs, 2400, 240)
-    utts, full = sharding.shard_utterances(s, fs, f0s, voiced5, fstep, 90.0, 62, plan, "sig")
-    assert len(utts) == 3 and all(u.group == "sig" and u.f0stale == full.f0stale for u in utts)
-    assert all(abs(u.group_std_det - np.std(s)) < 1e-15 for u in utts)
-    for u, (lo, hi, elo, ehi) in zip(utts, plan):
-        ft = engine.FrameTables(len(u.s), fs, u.f0s, u.voiced5, fstep, 62)
-        g = (elo + ft.ti0)                                        # global centre of the excerpt's frames
-        own = (g >= lo) & (g < hi)
-        gi = g[own] // step
-        # inside the owned range the excerpt sees the same frames, window lengths and harmonic counts
-        assert (ft.analysed[own] == full.analysed[gi]).all()
-        assert (ft.N[own] == full.N[gi]).all() and (ft.K0[own] == full.K0[gi]).all()
-        assert np.abs(ft.f0[own] - full.f0[gi]).max() < 1e-10
-        assert u.stat_range == (lo - elo, hi - elo)
+    voiced5[100:140] = False
+    full = engine.FrameTables(length, fs, f0s, voiced5, fstep, 62)
+    for lo, hi in ((0, 16000), (14400, 33600), (31200, length)):
+        e = full.excerpt(lo, hi)
+        g = lo // step
+        sl = slice(g, g + e.No_ti)
+        assert e.g0 == g and (e.ti0 + lo == full.ti0[sl]).all() and e.ti0[0] == 0
+        for name in ("f0", "K0", "N", "analysed", "isSpeech"):
+            assert (getattr(e, name) == getattr(full, name)[sl]).all()      # bitwise, not recomputed
+        assert e.f0stale == full.f0stale and e.own.sum() == hi - lo - e.ti0[0]
+        if hi == length:
+            assert g + e.No_ti == full.No_ti
+    with pytest.raises(ValueError):
+        full.excerpt(7, 16000)
 
 
 def test_merge_stats_equals_numpy_std():
@@ -74,7 +80,20 @@ def _worker(rank, world, port, q):
     rows = [(("g", "long"), float(len(data)), float(data.mean()), float(((data - data.mean()) ** 2).sum()))]
     merged = engine.merge_stats(sharding.make_allgather(dist)(rows))
     first, last = sharding.contiguous_blocks(7, world)[rank]
-    q.put((rank, merged[("g", "long")], (first, last)))
+    # neighbour exchange of per-frame parameter rows (longsignal.exchange_halo_rows) on CPU tensors over gloo:
+    # every rank owns 50 frames, keeps 8 halo rows per side; row content = global frame index
+    import torch
+    H, own, K = 8, 50, 5
+    f_lo, f_hi = rank * own, (rank + 1) * own
+    s_lo, s_hi = max(0, f_lo - H), min(world * own, f_hi + H)
+    gidx = torch.arange(s_lo, s_hi, dtype=torch.float64)
+    store = [torch.zeros((s_hi - s_lo, K), dtype=torch.float64) for _ in range(3)] + [torch.zeros(s_hi - s_lo, dtype=torch.float64)]
+    o0, o1 = f_lo - s_lo, f_hi - s_lo
+    for i, t in enumerate(store):
+        t[o0:o1] = (gidx[o0:o1] * (i + 1)).reshape((-1,) + (1,) * (t.dim() - 1))
+    sent = longsignal.exchange_halo_rows(store, (o0, o1), H, rank, world, dist)
+    ok = all(torch.equal(t, (gidx * (i + 1)).reshape((-1,) + (1,) * (t.dim() - 1)).expand_as(t)) for i, t in enumerate(store))
+    q.put((rank, merged[("g", "long")], (first, last), bool(ok), int(sent)))
     dist.destroy_process_group()
 
 
@@ -96,6 +115,7 @@ def test_world_size_2_gloo_statistics_exchange():
     d0 = np.random.default_rng(10).standard_normal(1000)
     d1 = np.random.default_rng(11).standard_normal(1500) + 1
     both = np.concatenate([d0, d1])
-    for rank, (n, mean, m2), blk in out:
+    for rank, (n, mean, m2), blk, halo_ok, sent in out:
+        assert halo_ok and sent == 8 * (3 * 5 + 1) * 8       # one neighbour each: 8 rows of 3*K+1 doubles
         assert n == len(both) and abs(mean - both.mean()) < 1e-13 and abs(np.sqrt(m2 / n) - np.std(both)) < 1e-13
-    assert [b for _, _, b in out] == [(0, 4), (4, 7)]       # every rank: same decision inputs, disjoint shard blocks
+    assert [o[2] for o in out] == [(0, 4), (4, 7)]       # every rank: same decision inputs, disjoint shard blocks
