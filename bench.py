@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shard-seconds S]
 
-Workload (config c2 of BASELINE.json): the synthetic 1-hour 16 kHz harmonic AM-FM signal
+Workload (config c2 of BASELINE.json): the synthetic 16 kHz harmonic AM-FM signal
 (f0(t) = 170 + 80 sin(2 pi 0.25 t + phi0), gender=(90,250)) is processed as
-contiguous frame-range shards; one STEP is the complete eaQHM analysis+synthesis (all
-adaptations until the SRER stops improving, functions.py:163-402) of ONE shard of
-`--shard-seconds` of audio per GPU.  The whole hour is 3600/S such steps; the full hour in one
-step would take minutes per step and the dense-track layout of this round needs 134 GB for it.
-With N GPUs every rank analyses its own shard (weak scaling, no data-path collective).
+contiguous frame ranges; one STEP is the complete eaQHM analysis+synthesis (all adaptations
+until the signal's SRER stops improving, functions.py:163-402) of the first N x S seconds of
+that signal, S = `--shard-seconds` of audio per GPU (weak scaling).  With N GPUs every rank owns
+one contiguous range; after every analysis pass the ranks exchange the per-frame parameters of
+their boundary frames with their neighbours (NCCL send/recv) and all-gather the residual
+statistics, so that all ranks take the reference's single convergence decision
+(eaqhm_b200/longsignal.py).  The whole hour is 3600/S such ranges; tools/run_full_hour.py streams
+it through one GPU with the same engine.
 
 Timed regions:  value = steps with the shard's inputs already resident in HBM (device time,
 CUDA events, max over ranks);  e2e = the same through the public API with host buffers
@@ -43,6 +46,16 @@ def shard_inputs(shard_index, seconds):
     base = cfg["f0_of_t"]
     off = shard_index * seconds
     s, f0s = synthetic.harmonic_signal(lambda t: base(t + off), seconds, fs=cfg["fs"], seed=1000 + shard_index)
+    n5 = len(np.arange(1, len(s), 80))
+    return dict(s=s, fs=cfg["fs"], f0s=f0s, voiced5=np.ones(n5, bool), frame_step=80, f0min=float(cfg["gender"][0]),
+                Kmax=int(round(int(cfg["fs"] / 2 - 200) / 90.0) + 10))   # min f0 of the whole hour (functions.py:120)
+
+
+def long_signal_inputs(seconds):
+    """The first `seconds` of the c2 signal (host arrays): samples, 5 ms f0 grid, flags."""
+    from eaqhm_b200 import synthetic
+    cfg = synthetic.config_c2(duration=seconds)
+    s, f0s = synthetic.make(cfg)
     n5 = len(np.arange(1, len(s), 80))
     return dict(s=s, fs=cfg["fs"], f0s=f0s, voiced5=np.ones(n5, bool), frame_step=80, f0min=float(cfg["gender"][0]),
                 Kmax=int(round(int(cfg["fs"] / 2 - 200) / 90.0) + 10))   # min f0 of the whole hour (functions.py:120)
@@ -140,17 +153,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    config = {"workload": "c2: synthetic 1-hour 16 kHz harmonic AM-FM signal (f0 90-250 Hz), one frame-range shard "
-                          "of %.0f s of audio per GPU per step, full eaQHM analysis+synthesis until SRER converges"
-                          % args.shard_seconds,
+    config = {"workload": "c2: synthetic 1-hour 16 kHz harmonic AM-FM signal (f0 90-250 Hz), its first %d x %.0f s as one "
+                          "contiguous frame range of %.0f s of audio per GPU per step, full eaQHM analysis+synthesis "
+                          "until the signal's SRER converges" % (world, args.shard_seconds, args.shard_seconds),
               "fs": 16000, "step": 15, "maxAdpt": 10, "shard_seconds": args.shard_seconds,
               "l2_policy": "per-step working set (dense tracks + Gram scratch, > 1 GB) exceeds the 126 MB L2",
-              "parallelism": "frame-range shards, one per GPU, no data-path collective"}
+              "parallelism": "contiguous frame ranges, one per GPU; per adaptation one neighbour exchange of the "
+                             "boundary frames' parameters (NCCL send/recv) and one all-gather of the SRER statistics"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        inp = shard_inputs(0, max(1.0, args.cpu_excerpt_seconds))
+        inp = long_signal_inputs(max(1.0, args.cpu_excerpt_seconds))
         times, last = [], None
         for i in range(args.warmup + args.steps):
             if i < args.warmup and i > 0:
@@ -189,6 +203,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    budget = int(args.scratch_gb * (1 << 30)) if args.scratch_gb > 0 else None
+    kw = {} if budget is None else dict(scratch_budget_bytes=budget)
     if args.workload == "c3":
         inps = corpus_inputs(rank * args.batch, args.batch)
         utts = [engine.Utterance(**i) for i in inps]
@@ -197,14 +213,16 @@ def main():
         config["workload"] = ("c3: batch of %d synthetic 3-second utterances at 16 kHz per GPU per step (utterance-sharded "
                               "corpus), full eaQHM analysis+synthesis until each utterance's SRER converges" % args.batch)
         config["parallelism"] = "utterance sharding, %d utterances per GPU per step, no data-path collective" % args.batch
+        make_engine = lambda: engine.Engine(utts, **kw)
     else:
-        inp = shard_inputs(rank, args.shard_seconds)
-        utts = [engine.Utterance(**inp)]
+        from eaqhm_b200 import longsignal
+        inp = long_signal_inputs(args.shard_seconds * world)
+        make_engine = lambda: longsignal.LongSignalEngine(shard_seconds=args.shard_seconds, rank=rank, world=world,
+                                                          dist=dist, **inp, **kw)
     L = _lib.lib()
 
     # ---------------- device-resident arm ----------------------------------------------------
-    budget = int(args.scratch_gb * (1 << 30)) if args.scratch_gb > 0 else None
-    eng = engine.Engine(utts, scratch_budget_bytes=budget)
+    eng = make_engine()
     for _ in range(args.warmup):
         res = eng.run_device()
     barrier()
@@ -224,10 +242,17 @@ def main():
     prof = _lib.profile_read()
     ms_dev = ev0.elapsed_time(ev1) / args.steps
     SRER, best_a, frames_solved = res
-    n_adapt = int(max(len(x) for x in SRER))
+    if args.workload == "c3":
+        n_adapt = int(max(len(x) for x in SRER))
+        srer_list = [float(x) for x in SRER[0]]
+        n_frames = int(sum(int(f.analysed.sum()) for f in eng.ft))
+        halo_bytes = 0
+    else:
+        n_adapt, srer_list = len(SRER), [float(x) for x in SRER]
+        n_frames, halo_bytes = eng.frames_owned, int(eng.exchanged_bytes)
     launches = sum(c for _, c in prof.values()) // args.steps
 
-    ft_list, useful_flops = eng.ft, eng.useful_flops
+    useful_flops = eng.useful_flops
     del eng
     torch.cuda.empty_cache()
 
@@ -235,7 +260,7 @@ def main():
     def e2e_step():
         # what a caller of the public batch API does: host arrays in, host results out; the engine (device buffers)
         # lives only inside the call
-        e = engine.Engine(utts, scratch_budget_bytes=budget)
+        e = make_engine()
         r = e.run()
         return int(e.h2d_bytes), int(e.d2h_bytes), r
     for _ in range(max(2, min(args.warmup, 3))):
@@ -256,7 +281,6 @@ def main():
     e2e_value = audio / t_e2e
 
     # ---------------- roofline of the dominant kernel ------------------------------------------
-    n_frames = int(sum(int(f.analysed.sum()) for f in ft_list))
     # algorithmic flops: accumulated on the device by k_active from the actual active-harmonic counts of every
     # frame solve; adaptation 0 uses Toeplitz tables instead of the Gram and is not counted there
     useful = useful_flops
@@ -277,9 +301,9 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": dict(config, adaptations_run=n_adapt, frames_per_shard=n_frames,
-                                               frame_solves_per_step=int(frames_solved),
-                                               SRER_dB=[float(x) for x in SRER[0]]),
+           "data": "synthetic", "config": dict(config, adaptations_run=n_adapt, frames_per_gpu=n_frames,
+                                               frame_solves_per_gpu_per_step=int(frames_solved),
+                                               halo_bytes_sent_per_gpu_per_step=halo_bytes, SRER_dB=srer_list),
            "frame_solves_per_s": frames_solved * world / (ms_dev * 1e-3),
            "realtime_factor_per_gpu": value / world,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from .engine import BufferPool, Engine, Result, Utterance, _to_host, merge_stats
 from .host import FrameTables
-from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks, make_allgather
+from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks
 
 NROW = 4      # stores: am, ph, fm [rows][Kmax] + a0 [rows]
 
@@ -96,6 +96,15 @@ def exchange_halo_rows(store, own_rows, halo_rows, rank, world, dist):
     for inc, r0 in recvs:
         unpack(inc, r0)
     return sent
+
+
+def allgather_rows(rows, world, dist):
+    """All ranks' (n, mean, M2) rows in rank order: one fixed-size all-gather (NCCL on GPUs, gloo in the CPU test)."""
+    if dist is None or world == 1:
+        return rows
+    parts = [torch.empty_like(rows) for _ in range(world)]
+    dist.all_gather(parts, rows.contiguous())
+    return torch.cat(parts, dim=0)
 
 
 class LongSignalEngine:
@@ -191,6 +200,9 @@ class LongSignalEngine:
         ones = np.ones(1, bool)
         nsh = len(self.shards)
         stat_dev = torch.zeros((nsh, 2), dtype=torch.float64, device=self.device)
+        # (n, mean, M2) of this rank's shards, padded to the largest shard count of any rank (n = 0 rows are ignored)
+        rows_dev = torch.zeros((max(len(p) for p in self.plan_all), 3), dtype=torch.float64, device=self.device)
+        rows_dev[:nsh, 0] = torch.tensor([sh["n_stat"] for sh in self.shards], dtype=torch.float64)
         self.pool.get("status", 2, torch.int32).zero_()
         self.pool.get("flops", 3, torch.float64).zero_()
         self.exchanged_bytes = 0
@@ -231,12 +243,10 @@ class LongSignalEngine:
                 for i in range(3):
                     self.cand[i][r0 + l0:r0 + l1].copy_(e.best[i].view(G, K)[l0:l1])
                 self.cand[3][r0 + l0:r0 + l1].copy_(e.best[3][l0:l1])
-            stat = stat_dev.cpu().numpy()                                      # the one host sync per adaptation
+            rows_dev[:nsh, 1:].copy_(stat_dev)
+            stat = allgather_rows(rows_dev, self.world, self.dist).cpu().numpy()   # the one host sync per adaptation
             self.d2h_bytes += stat.nbytes
-            rows = [("long", self.shards[j]["n_stat"], stat[j, 0], stat[j, 1]) for j in range(nsh)]
-            if self.dist is not None and self.world > 1:
-                rows = make_allgather(self.dist)(rows)
-            n, _, m2 = merge_stats(rows)["long"]
+            n, _, m2 = merge_stats([("long", r[0], r[1], r[2]) for r in stat if r[0] > 0])["long"]
             with np.errstate(all="ignore"):
                 srer = 20 * np.log10(self.std_det / np.sqrt(m2 / n))           # functions.py:388
             SRER.append(srer)

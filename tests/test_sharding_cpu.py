@@ -93,6 +93,12 @@ def _worker(rank, world, port, q):
         t[o0:o1] = (gidx[o0:o1] * (i + 1)).reshape((-1,) + (1,) * (t.dim() - 1))
     sent = longsignal.exchange_halo_rows(store, (o0, o1), H, rank, world, dist)
     ok = all(torch.equal(t, (gidx * (i + 1)).reshape((-1,) + (1,) * (t.dim() - 1)).expand_as(t)) for i, t in enumerate(store))
+    # fixed-size all-gather of the (n, mean, M2) rows, padded with n = 0 rows (longsignal.allgather_rows)
+    rt = torch.zeros((3, 3), dtype=torch.float64)
+    rt[0] = torch.tensor(rows[0][1:], dtype=torch.float64)
+    allr = longsignal.allgather_rows(rt, world, dist).numpy()
+    m2 = engine.merge_stats([("x", r[0], r[1], r[2]) for r in allr if r[0] > 0])["x"]
+    ok = ok and len(allr) == 3 * world and np.allclose(m2, merged[("g", "long")], rtol=1e-15, atol=0)
     q.put((rank, merged[("g", "long")], (first, last), bool(ok), int(sent)))
     dist.destroy_process_group()
 

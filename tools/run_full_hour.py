@@ -1,39 +1,80 @@
-"""One-off: the WHOLE config-c2 signal (3600 s, 16 kHz) on one GPU as consecutive frame-range shards, each analysed
-completely (shard-local stopping).  Prints one JSON line with the total device time and audio-s/s.  Synthetic shard
-generation on the host is excluded from the timed region (it is preprocessing) but reported."""
+"""The WHOLE config-c2 signal (3600 s, 16 kHz, 3.84 M frames) on ONE GPU through the streamed long-signal engine
+(eaqhm_b200/longsignal.py): per-frame parameter store resident, dense tracks rebuilt shard by shard, ONE global SRER
+decision per adaptation exactly like the reference's loop (functions.py:388,394-396).  Prints one JSON line.
+The synthetic signal is generated with torch on the device (same formula and random draws as
+eaqhm_b200/synthetic.py:harmonic_signal, which would need minutes of host time for 57.6 M samples) and handed to the
+engine as a host array; generation is outside the timed region.
+Usage: python tools/run_full_hour.py [shard_seconds] [total_seconds] [maxAdpt]"""
 import json, os, sys, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-import bench
-from eaqhm_b200 import engine
+from eaqhm_b200 import _lib, longsignal, synthetic
 
 shard_s = float(sys.argv[1]) if len(sys.argv) > 1 else 20.0
 total_s = float(sys.argv[2]) if len(sys.argv) > 2 else 3600.0
-n = int(round(total_s / shard_s))
-t_gen = t_gpu = 0.0
-solves = 0
-adapt_hist = {}
-srer_w = 0.0
+maxAdpt = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+
+
+def signal_on_device(cfg, duration, noise_db=-50.0, peak=0.5):
+    fs, rng = cfg["fs"], np.random.default_rng(cfg["seed"])
+    length = int(round(duration * fs))
+    dev = torch.device("cuda")
+    t = torch.arange(length, dtype=torch.float64, device=dev) / fs
+    f0 = torch.from_numpy(np.asarray(cfg["f0_of_t"](np.arange(length) / fs), float)).to(dev)
+    phi = 2 * np.pi * torch.cumsum(f0, 0) / fs
+    Kmax = int(np.floor((fs / 2 - 200) / float(f0.min())))
+    s = torch.zeros(length, dtype=torch.float64, device=dev)
+    for k in range(1, Kmax + 1):
+        theta, r, d, p = rng.uniform(-np.pi, np.pi), rng.uniform(2.0, 6.0), rng.uniform(0.0, 0.3), rng.uniform(-np.pi, np.pi)
+        amp = (1.0 / k) * (1.0 + d * torch.sin(2 * np.pi * r * t + p))
+        amp = torch.where(k * f0 <= fs / 2 - 200, amp, torch.zeros_like(amp))
+        s += amp * torch.cos(k * phi + theta)
+    s *= peak / float(s.abs().max())
+    s += torch.from_numpy(rng.standard_normal(length)).to(dev) * peak * 10 ** (noise_db / 20)
+    s = torch.clamp(torch.round(s * 32768), -32768, 32767) / 32768
+    tg = synthetic.f0_grid_times(length, fs)
+    f0s = np.stack([tg, np.asarray(cfg["f0_of_t"](tg), float), np.ones_like(tg)], axis=1)
+    return s.cpu().numpy(), f0s
+
+
+t0 = time.perf_counter()
+cfg = synthetic.config_c2(duration=total_s)
+s, f0s = signal_on_device(cfg, total_s)
+torch.cuda.empty_cache()
+n5 = len(np.arange(1, len(s), 80))
+t_gen = time.perf_counter() - t0
+t0 = time.perf_counter()
+eng = longsignal.LongSignalEngine(s, 16000, f0s, np.ones(n5, bool), 80, 90.0, int(round(7800 / 90.0) + 10),
+                                  shard_seconds=shard_s, maxAdpt=maxAdpt)
+torch.cuda.synchronize()
+t_setup = time.perf_counter() - t0
+L = _lib.lib()
+L.eaqhm_profile_reset(); L.eaqhm_profile_enable(1)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for i in range(n):
-    t0 = time.perf_counter()
-    inp = bench.shard_inputs(i, shard_s)
-    t_gen += time.perf_counter() - t0
-    eng = engine.Engine([engine.Utterance(**inp)])
-    torch.cuda.synchronize()
-    ev0.record()
-    SRER, best_a, fs_ = eng.run_device()
-    ev1.record()
-    torch.cuda.synchronize()
-    t_gpu += ev0.elapsed_time(ev1) * 1e-3
-    solves += fs_
-    adapt_hist[len(SRER[0])] = adapt_hist.get(len(SRER[0]), 0) + 1
-    srer_w += max(SRER[0])
-    del eng
-    if i % 20 == 0:
-        print("shard %d/%d  gpu %.1f s  gen %.1f s" % (i, n, t_gpu, t_gen), file=sys.stderr, flush=True)
-print(json.dumps({"workload": "c2 full signal as %d shards of %.0f s" % (n, shard_s), "audio_seconds": n * shard_s,
-                  "gpu_seconds": t_gpu, "audio_s_per_s": n * shard_s / t_gpu, "frame_solves": solves,
-                  "frame_solves_per_s": solves / t_gpu, "adaptations_histogram": adapt_hist,
-                  "mean_best_SRER_dB": srer_w / n, "host_signal_generation_seconds": t_gen}))
+
+
+def progress(a, SRER):
+    print("adaptation %d  SRER %.6f dB" % (a, SRER[-1]), file=sys.stderr, flush=True)
+
+
+ev0.record()
+SRER, best_a, solves = eng.run_device(progress)
+ev1.record()
+torch.cuda.synchronize()
+t_gpu = ev0.elapsed_time(ev1) * 1e-3
+L.eaqhm_profile_enable(0)
+prof = {k: round(v[0] * 1e-3, 3) for k, v in _lib.profile_read().items()}
+t0 = time.perf_counter()
+res = eng.results(SRER, best_a, solves)
+t_out = time.perf_counter() - t0
+srer_check = 20 * np.log10(np.std(s) / np.std(s - res.s_recon))
+print(json.dumps({"workload": "c2 whole signal, %d shards of %.0f s streamed through one GPU, global SRER decision"
+                              % (len(eng.shards), shard_s),
+                  "audio_seconds": total_s, "gpu_seconds": t_gpu, "audio_s_per_s": total_s / t_gpu,
+                  "frames": int(eng.full.No_ti), "frame_solves": int(solves), "frame_solves_per_s": solves / t_gpu,
+                  "adaptations_run": len(SRER), "SRER_dB": [float(x) for x in SRER], "best_adaptation": int(best_a),
+                  "SRER_of_returned_waveform_dB": float(srer_check),
+                  "device_memory_peak_GiB": torch.cuda.max_memory_allocated() / 2 ** 30,
+                  "kernel_seconds": prof, "host_signal_generation_seconds": t_gen, "engine_setup_seconds": t_setup,
+                  "result_readback_seconds": t_out, "not_pd_frames": res.stats["not_pd_frames"]}))
