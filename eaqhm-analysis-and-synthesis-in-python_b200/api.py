@@ -55,10 +55,24 @@ def make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender="other", ste
                      frame_step=int(frame_step), f0min=float(f0min), Kmax=int(Kmax), det_part=det)
 
 
+STREAM_THRESHOLD_BYTES = 8 << 30     # dense tracks (3 x Kmax x length doubles) above this are streamed shard by shard
+
+
 def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10,
-                   pitchPeriods=3, analysisWindow=32, fullWaveform=True, partials=0, on_adaptation=None):
-    """The hot path on array-level inputs; returns an engine.Result."""
+                   pitchPeriods=3, analysisWindow=32, fullWaveform=True, partials=0, on_adaptation=None,
+                   stream_threshold_bytes=None, shard_seconds=20.0):
+    """The hot path on array-level inputs; returns an engine.Result.  Signals whose dense
+    per-sample tracks would not fit comfortably (the reference's layout needs length x Kmax x 7 doubles,
+    functions.py:159-171) go through the streamed long-signal engine, which gives the same result."""
     u = make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender, step, analysisWindow, fullWaveform, partials)
+    limit = STREAM_THRESHOLD_BYTES if stream_threshold_bytes is None else stream_threshold_bytes
+    if 3 * 8 * u.Kmax * len(u.s) > limit:
+        from .longsignal import LongSignalEngine
+        eng = LongSignalEngine(u.s, u.fs, u.f0s, u.voiced5, u.frame_step, u.f0min, u.Kmax, shard_seconds=shard_seconds,
+                               det_part=u.det_part, step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods,
+                               analysisWindow=analysisWindow)
+        cb = None if on_adaptation is None else (lambda a, SRER: on_adaptation(a, [SRER]))
+        return eng.run(cb)
     eng = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow)
     return eng.run(on_adaptation)[0]
 

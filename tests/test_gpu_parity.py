@@ -383,6 +383,20 @@ def test_api_drop_in_on_sa19_with_supplied_preprocessing(tmp_path):
     assert abs(float(d.amplitudes[0][0]) - g["det_am"][i, 0]) <= 1e-9 * g["det_am"][i].max()
 
 
+def test_api_streams_long_signals_with_the_same_result():
+    """analyze_arrays switches to the streamed long-signal engine when the dense tracks would be too large; forced
+    here on SA19 (threshold 0, 1 s shards): the published SRER values and the reference's waveform come out."""
+    from eaqhm_b200 import api
+    g, kw = load_golden("sa19")
+    s = g["pcm"].astype(float) / 32768
+    res = api.analyze_arrays(s, int(g["fs"]), g["f0s"], g["speech5"], g["voiced5"], int(g["frame_step"]), "female",
+                             stream_threshold_bytes=0, shard_seconds=1.0)
+    assert res.stats["shards"] == 4 and len(res.SRER) == 6
+    assert np.abs(np.array(res.SRER) - g["SRER"]).max() <= 1e-8 and np.abs(res.s_recon - g["s_recon"]).max() <= TOL_S
+    out = compare_to_golden(res, g)
+    assert out["flags_ok"] and out["support_equal"] and out["am_rel_framemax"] <= TOL_REL and out["fm_rel_strong"] <= TOL_REL
+
+
 def test_api_drop_in_from_wav_only(tmp_path):
     """The full drop-in: wav path + gender, nothing supplied; host preprocessing (SWIPE', flags) restated in
     preprocess.py, hot path on the GPU.  Must give the published SA19 SRER values."""
