@@ -239,6 +239,25 @@ def test_batch_equals_single_runs_bitwise():
         assert (a.fm == b.fm[:, :a.fm.shape[1]]).all() and (a.ph == b.ph[:, :a.ph.shape[1]]).all()
 
 
+def test_corpus_runner_equals_single_runs_bitwise():
+    """Config c3/c5 mechanics: a corpus dealt round-robin over ranks and analysed in memory-sized batches with host
+    preprocessing running ahead in threads gives every utterance the result of its own single run."""
+    from eaqhm_b200 import corpus, synthetic
+    inps = [synth_inputs(synthetic.config_c3(20 + i, duration=0.25 + 0.05 * (i % 3)), maxAdpt=2) for i in range(5)]
+    singles = [run_cuda(i) for i in inps]
+    budget = corpus.utterance_bytes(utterance(inps[0])) * 2 + 1000         # forces several batches
+    seen = {}
+    for world in (1, 2):
+        for rank in range(world):
+            for i, r in corpus.analyze_corpus(len(inps), lambda i: utterance(inps[i]), rank=rank, world=world,
+                                              batch_bytes=budget, maxAdpt=2, workers=2, lookahead=3):
+                seen[(world, i)] = r
+    for world in (1, 2):
+        for i, a in enumerate(singles):
+            b = seen[(world, i)]
+            assert a.SRER == b.SRER and (a.s_recon == b.s_recon).all() and (a.am == b.am).all() and (a.fm == b.fm).all()
+
+
 def test_chunked_analysis_equals_unchunked_bitwise():
     from eaqhm_b200 import synthetic
     inp = synth_inputs(synthetic.config_c3(9, duration=0.3), maxAdpt=2)

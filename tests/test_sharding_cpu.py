@@ -7,7 +7,7 @@ import socket
 import numpy as np
 import pytest
 
-from eaqhm_b200 import engine, longsignal, sharding
+from eaqhm_b200 import corpus, engine, longsignal, sharding
 
 
 def test_partitions_cover_everything_once():
@@ -17,6 +17,19 @@ def test_partitions_cover_everything_once():
         cb = sharding.contiguous_blocks(n, w)
         assert cb[0][0] == 0 and cb[-1][1] == n and all(a[1] == b[0] for a, b in zip(cb, cb[1:]))
         assert max(b - a for a, b in cb) - min(b - a for a, b in cb) <= 1
+
+
+def test_corpus_batches_respect_the_memory_budget():
+    sizes, kmaxes = [48000, 48000, 16000, 96000, 48000, 1000], [60, 97, 40, 97, 50, 97]
+    per = lambda n, k: (3 * k + 4) * n * 8
+    budget = per(48000 + 48000 + 16000, 97)
+    plan = corpus.plan_batches(sizes, kmaxes, budget)
+    assert plan[0][0] == 0 and plan[-1][1] == len(sizes) and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+    for a, b in plan:
+        assert b - a == 1 or per(sum(sizes[a:b]), max(kmaxes[a:b])) <= budget
+    assert plan[0] == (0, 3)
+    assert corpus.plan_batches([10 ** 9], [97], 1) == [(0, 1)]          # an oversized utterance still gets a batch
+    assert corpus.plan_batches([], [], 1) == []
 
 
 def test_range_plan_alignment_and_cover():
