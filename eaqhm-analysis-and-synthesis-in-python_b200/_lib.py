@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeaqhm_b200.so")
+# EAQHM_LIB: load another build of the same sources (kernel experiments: tools/build_variant.sh); default in-tree
+LIB_PATH = os.environ.get("EAQHM_LIB") or os.path.join(_HERE, "libeaqhm_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -595,6 +595,7 @@ constexpr int kG2Warps = 4;
 constexpr int kG2StageDoubles = 2 /*panel*/ * 2 /*plane*/ * 16 * kG2P;
 constexpr int kGram2Smem = kG2Warps * 2 /*stages*/ * kG2StageDoubles * 8;
 
+template <bool k3M>
 __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int items_per_frame) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -624,7 +625,11 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
             for (int sj = 0; sj < 2; sj++)
                 act_[si][sj] = (i0 + si * 8 < Mx) && (j0 + sj * 8 < Mx) && (j0 + sj * 8 <= i0 + si * 8);
 
-        double acc[2][2][3][2][2];
+        // plain: acc[..][0] = real part, [1] = imaginary part (4 real products per complex product).
+        // 3M:    acc[..][0] = Xr^T Xr', [1] = Xi^T Xi', [2] = (Xr - Xi)^T (Xr' + Xi'): 3 real products;
+        //        Re = [0] + [1], Im = [2] - [0] + [1]  (normwise as accurate as the 4-product form)
+        constexpr int kAcc = k3M ? 3 : 2;
+        double acc[2][2][3][kAcc][2];
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
 #pragma unroll
                 for (int c = 0; c < 3; c++)
 #pragma unroll
-                    for (int d = 0; d < 2; d++) acc[a][b][c][d][0] = acc[a][b][c][d][1] = 0.0;
+                    for (int d = 0; d < kAcc; d++) acc[a][b][c][d][0] = acc[a][b][c][d][1] = 0.0;
 
         // stage loader: panel 0 = tile rows' columns, panel 1 = tile cols' columns (skipped on the diagonal);
         // per (panel, plane): 16 cols x 16 samples = 128 pieces of 16 B -> 4 per lane
@@ -679,18 +684,19 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
 #pragma unroll
             for (int kk = 0; kk < kG2K; kk += 4) {
                 const double nc = (double)(c * kG2K + kk + lc - N), nc2 = nc * nc;
-                double ar[2], ai[2], nai[2], br[2][3], bi[2][3];
+                double ar[2], ai[2], ax[2], br[2][3], bi[2][3], bx[2][3];
 #pragma unroll
                 for (int si = 0; si < 2; si++) {
                     ar[si] = ar_s[si * 8 * kG2P + kk];
                     ai[si] = ai_s[si * 8 * kG2P + kk];
-                    nai[si] = -ai[si];
+                    ax[si] = k3M ? ar[si] - ai[si] : -ai[si];
                 }
 #pragma unroll
                 for (int sj = 0; sj < 2; sj++) {
                     const double r = br_s[sj * 8 * kG2P + kk], i = bi_s[sj * 8 * kG2P + kk];
                     br[sj][0] = r; br[sj][1] = r * nc; br[sj][2] = r * nc2;
                     bi[sj][0] = i; bi[sj][1] = i * nc; bi[sj][2] = i * nc2;
+                    if (k3M) { const double t = r + i; bx[sj][0] = t; bx[sj][1] = t * nc; bx[sj][2] = t * nc2; }
                 }
 #pragma unroll
                 for (int si = 0; si < 2; si++)
@@ -699,10 +705,16 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
                         if (act_[si][sj]) {
 #pragma unroll
                             for (int wt = 0; wt < 3; wt++) {
-                                dmma884(acc[si][sj][wt][0], ar[si], br[sj][wt]);
-                                dmma884(acc[si][sj][wt][1], ar[si], bi[sj][wt]);
-                                dmma884(acc[si][sj][wt][0], ai[si], bi[sj][wt]);
-                                dmma884(acc[si][sj][wt][1], nai[si], br[sj][wt]);
+                                if (k3M) {
+                                    dmma884(acc[si][sj][wt][0], ar[si], br[sj][wt]);
+                                    dmma884(acc[si][sj][wt][1], ai[si], bi[sj][wt]);
+                                    dmma884(acc[si][sj][wt][kAcc - 1], ax[si], bx[sj][wt]);
+                                } else {
+                                    dmma884(acc[si][sj][wt][0], ar[si], br[sj][wt]);
+                                    dmma884(acc[si][sj][wt][1], ar[si], bi[sj][wt]);
+                                    dmma884(acc[si][sj][wt][0], ai[si], bi[sj][wt]);
+                                    dmma884(acc[si][sj][wt][1], ax[si], br[sj][wt]);
+                                }
                             }
                         }
             }
@@ -722,9 +734,11 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
                 for (int e = 0; e < 2; e++) {
                     const int j = j0 + sj * 8 + 2 * lc + e;
                     if (i >= Mx || j >= Mx) continue;
-                    const double2 a = make_double2(acc[si][sj][0][0][e], acc[si][sj][0][1][e]);
-                    const double2 b = make_double2(acc[si][sj][1][0][e], acc[si][sj][1][1][e]);
-                    const double2 cc = make_double2(acc[si][sj][2][0][e], acc[si][sj][2][1][e]);
+                    auto cplx = [&](int wt) {
+                        const double p0 = acc[si][sj][wt][0][e], p1 = acc[si][sj][wt][1][e];
+                        return k3M ? make_double2(p0 + p1, (acc[si][sj][wt][kAcc - 1][e] - p0) + p1) : make_double2(p0, p1);
+                    };
+                    const double2 a = cplx(0), b = cplx(1), cc = cplx(2);
                     if (j <= i) {
                         RF[(size_t)i * Pp + j] = a;
                         RF[(size_t)(Mx + i) * Pp + Mx + j] = cc;
@@ -815,8 +829,15 @@ __device__ unsigned long long g_chol_cycles[8];
 #define TMARK(slot) do { } while (0)
 #endif
 
+#ifndef EAQHM_CHOL_3M
+#define EAQHM_CHOL_3M 0
+#endif
+constexpr bool kChol3M = EAQHM_CHOL_3M != 0;
 template <int kNW>
-__global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(SolveArgs A) {
+#ifndef EAQHM_CHOL_THREADS_PER_SM
+#define EAQHM_CHOL_THREADS_PER_SM 512
+#endif
+__global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 32)) k_chol_solve(SolveArgs A) {
     constexpr int kThreads = kNW * 32;
     const int jl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane >> 2, lc = lane & 3;
@@ -847,11 +868,15 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
             const int i0 = rb * kNb;
             if (have) {
                 // ---- 1. DMMA update of the 16x16 tile ---------------------------------------------
-                double wr[2][2][2], wi[2][2][2];
+                // plain: wr, wi accumulate the real and imaginary parts (4 DMMA per complex 8x8x4 product).
+                // 3M (kChol3M): wr = -sum ar br, wi = -sum ai bi, wx = -sum (ar + ai)(br - bi) (3 DMMA); afterwards
+                // Re = wr + wi, Im = wx - wr + wi.
+                double wr[2][2][2], wi[2][2][2], wx[2][2][2];
 #pragma unroll
                 for (int a = 0; a < 2; a++)
 #pragma unroll
-                    for (int b = 0; b < 2; b++) wr[a][b][0] = wr[a][b][1] = wi[a][b][0] = wi[a][b][1] = 0.0;
+                    for (int b = 0; b < 2; b++)
+                        wr[a][b][0] = wr[a][b][1] = wi[a][b][0] = wi[a][b][1] = wx[a][b][0] = wx[a][b][1] = 0.0;
                 if (jb > 0) {
                     const double2* arow[2];
                     const double2* brow[2];
@@ -865,16 +890,42 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_solve(Solve
                         double2 a[2], b[2];
 #pragma unroll
                         for (int s2 = 0; s2 < 2; s2++) { a[s2] = arow[s2][k0]; b[s2] = brow[s2][k0]; }
+                        if (kChol3M) {
+                            double as[2], bd[2];
+#pragma unroll
+                            for (int s2 = 0; s2 < 2; s2++) { as[s2] = -(a[s2].x + a[s2].y); bd[s2] = b[s2].x - b[s2].y; }
+#pragma unroll
+                            for (int si = 0; si < 2; si++)
+#pragma unroll
+                                for (int sj = 0; sj < 2; sj++) {
+                                    dmma884(wr[si][sj], -a[si].x, b[sj].x);
+                                    dmma884(wi[si][sj], -a[si].y, b[sj].y);
+                                    dmma884(wx[si][sj], as[si], bd[sj]);
+                                }
+                        } else {
+#pragma unroll
+                            for (int si = 0; si < 2; si++)
+#pragma unroll
+                                for (int sj = 0; sj < 2; sj++) {
+                                    // W -= a * conj(b):  Wr -= ar br + ai bi ; Wi -= ai br - ar bi
+                                    dmma884(wr[si][sj], -a[si].x, b[sj].x);
+                                    dmma884(wi[si][sj], -a[si].y, b[sj].x);
+                                    dmma884(wr[si][sj], -a[si].y, b[sj].y);
+                                    dmma884(wi[si][sj], a[si].x, b[sj].y);
+                                }
+                        }
+                    }
+                    if (kChol3M) {
 #pragma unroll
                         for (int si = 0; si < 2; si++)
 #pragma unroll
-                            for (int sj = 0; sj < 2; sj++) {
-                                // W -= a * conj(b):  Wr -= ar br + ai bi ; Wi -= ai br - ar bi
-                                dmma884(wr[si][sj], -a[si].x, b[sj].x);
-                                dmma884(wi[si][sj], -a[si].y, b[sj].x);
-                                dmma884(wr[si][sj], -a[si].y, b[sj].y);
-                                dmma884(wi[si][sj], a[si].x, b[sj].y);
-                            }
+                            for (int sj = 0; sj < 2; sj++)
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    const double p1 = wr[si][sj][e], p2 = wi[si][sj][e];
+                                    wr[si][sj][e] = p1 + p2;
+                                    wi[si][sj][e] = (wx[si][sj][e] - p1) + p2;
+                                }
                     }
                 }
                 __syncwarp();
@@ -1090,7 +1141,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
         gram_attr = true;
     }
-    // experiment knob (tools only): EAQHM_GRAM_VARIANT=1 selects the CTA-tiled kernel
+    // experiment knob (tools only): EAQHM_GRAM_VARIANT=1 selects the CTA-tiled kernel, 3 the warp kernel with four real
+    // products per complex product; default: warp kernel with three (3M)
     static int gram_variant = getenv("EAQHM_GRAM_VARIANT") ? atoi(getenv("EAQHM_GRAM_VARIANT")) : 0;
     if (do_gram && gram_variant == 1) {
         const int Tt = (a.Mxmax + kGT - 1) / kGT;
@@ -1100,7 +1152,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         static bool g2_attr = false;
         static int nsm = 148;
         if (!g2_attr) {
-            CUDA_TRY(cudaFuncSetAttribute(k_gram_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
             int dev = 0;
             CUDA_TRY(cudaGetDevice(&dev));
             CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -1110,7 +1163,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         const long long nitems = (long long)a.nf * ipf;
         int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
         if ((long long)blocks * kG2Warps > nitems) blocks = (int)((nitems + kG2Warps - 1) / kG2Warps);
-        LAUNCH(KC_GRAM, st, k_gram_warp<<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
+        if (gram_variant == 3) LAUNCH(KC_GRAM, st, k_gram_warp<false><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
+        else LAUNCH(KC_GRAM, st, k_gram_warp<true><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
     }
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame

@@ -28,9 +28,8 @@ class Utterance:
     f0min: float                    # lower pitch limit (functions.py:95-109)
     Kmax: int                       # functions.py:117-120
     det_part: np.ndarray = None     # SRER target (functions.py:138,146); default s
-    # frame-range shards of one long signal (sharding.py): the shards of a signal share `group`, count only
-    # their owned samples `stat_range` in the SRER, and use the whole signal's target std / stale f0 (Q1)
-    group: object = None
+    # excerpts of one long signal (longsignal.py) count only their owned samples `stat_range` in the SRER statistics
+    # and use the whole signal's target std / stale f0 (Q1)
     stat_range: tuple = None
     group_std_det: float = None
     f0stale: float = None
@@ -132,7 +131,7 @@ class Engine:
     """Holds the device buffers of one batch and runs the adaptation loop."""
 
     def __init__(self, utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32,
-                 device="cuda", chunk=None, scratch_budget_bytes=None, stats_allgather=None, frame_tables=None,
+                 device="cuda", chunk=None, scratch_budget_bytes=None, frame_tables=None,
                  pool=None):
         if not torch.cuda.is_available():
             raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
@@ -178,9 +177,6 @@ class Engine:
         self.t_xoff = _dev([int(u.xoff) for u in self.utts], np.int64, d)
         self.t_stat_lo = _dev([lo for lo, _ in sr], np.int64, d)
         self.t_stat_hi = _dev([hi for _, hi in sr], np.int64, d)
-        # SRER groups: utterances (shards) that share one convergence decision (functions.py:388,394-396)
-        self.group = [("u", i) if u.group is None else ("g", u.group) for i, u in enumerate(self.utts)]
-        self.stats_allgather = stats_allgather
         self.t_f0min = _dev([float(u.f0min) for u in self.utts], np.float64, d)
         self.t_active = torch.ones(U, dtype=torch.uint8, device=d)
         # frames each utterance analyses: all gated frames (functions.py:180-181), or for an excerpt of a streamed
@@ -316,17 +312,10 @@ class Engine:
                                            self._stream()))
         return self.stat
 
-    def group_srer(self, stat):
-        """SRER per utterance from the per-utterance (n, mean, M2): utterances of one group (the shards of a
-        long signal, possibly on other ranks) are merged with the pairwise-variance formula."""
-        U = self.U
-        rows = [(self.group[u], self.stat_n[u], stat[u], stat[U + u]) for u in range(U)]
-        if self.stats_allgather is not None:
-            rows = self.stats_allgather(rows)
-        acc = merge_stats(rows)
+    def srer(self, stat):
+        """SRER per utterance (functions.py:388) from the residual statistics [mean | M2] of eaqhm_synthesize."""
         with np.errstate(all="ignore"):
-            return np.array([20 * np.log10(self.std_det[u] / np.sqrt(acc[self.group[u]][2] / acc[self.group[u]][0]))
-                             for u in range(U)])                          # functions.py:388
+            return 20 * np.log10(self.std_det / np.sqrt(stat[self.U:] / self.stat_n))
 
     def snapshot(self, improved):
         self.improved.copy_(torch.from_numpy(np.asarray(improved, bool).astype(np.uint8)))
@@ -353,7 +342,7 @@ class Engine:
             self.interpolate()
             stat = self.synthesize().cpu().numpy()                          # the one host sync per adaptation
             self.d2h_bytes += stat.nbytes
-            srer_u = self.group_srer(stat)
+            srer_u = self.srer(stat)
             improved = np.zeros(U, bool)
             with np.errstate(all="ignore"):
                 for u in np.flatnonzero(active):

@@ -21,13 +21,3 @@ def contiguous_blocks(n_items, world):
         out.append((start, start + cnt))
         start += cnt
     return out
-
-
-def make_allgather(dist):
-    """Row gatherer over a torch.distributed process group (NCCL or gloo): every rank contributes a list of
-    (group, n, mean, M2) rows and receives all of them in rank order."""
-    def gather(rows):
-        out = [None] * dist.get_world_size()
-        dist.all_gather_object(out, rows)
-        return [r for part in out for r in part]
-    return gather

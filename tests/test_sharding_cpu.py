@@ -91,7 +91,9 @@ def _worker(rank, world, port, q):
     rng = np.random.default_rng(10 + rank)
     data = rng.standard_normal(1000 + 500 * rank) + rank
     rows = [(("g", "long"), float(len(data)), float(data.mean()), float(((data - data.mean()) ** 2).sum()))]
-    merged = engine.merge_stats(sharding.make_allgather(dist)(rows))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, rows)
+    merged = engine.merge_stats([r for part in gathered for r in part])
     first, last = sharding.contiguous_blocks(7, world)[rank]
     # neighbour exchange of per-frame parameter rows (longsignal.exchange_halo_rows) on CPU tensors over gloo:
     # every rank owns 50 frames, keeps 8 halo rows per side; row content = global frame index
