@@ -36,7 +36,7 @@ class Tables(C.Structure):
 
 class Tracks(C.Structure):
     """eaqhm_tracks."""
-    _fields_ = [("am", C.c_void_p), ("ph", C.c_void_p), ("fmc", C.c_void_p)]
+    _fields_ = [("am", C.c_void_p), ("ph", C.c_void_p), ("fmc", C.c_void_p), ("zc", C.c_void_p), ("zs", C.c_void_p)]
 
 
 class Knots(C.Structure):

@@ -16,6 +16,8 @@ struct AnaArgs {
     const double* s;
     const double* am_cur;
     const double* fm_cur;
+    const double* zc_cur;           // cos / sin of the phase track (eaqhm_tracks.zc, .zs)
+    const double* zs_cur;
     eaqhm_knots k;
     double* best_am;
     int32_t adapt;
@@ -219,17 +221,82 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
             //    in-place fallback writes of this and earlier frames (Q6, functions.py:209-210)
             const double* fmk = A.fm_cur + (int64_t)k * A.t.T + us;
             const double* amk = A.am_cur + (int64_t)k * A.t.T + us;
+            bool clean = A.zc_cur != nullptr && cl - N >= 0;   // no wrapped indices, no zeros, no fallback substitution
             for (int n = lane; n < L; n += 32) {
                 int64_t il = cl - N + n;
                 if (il < 0) il += ul;
                 double f = fmk[il], a = amk[il];
                 if (k == 0 && (il % A.t.step) == 0) {
                     const int64_t gi = A.t.gfirst[u] + il / A.t.step;
-                    if (gi <= g && gi < A.t.gfirst[u] + A.t.gcount[u] && A.fb[gi]) { f = kFallbackFm; a = kFallbackAm; }
+                    if (gi <= g && gi < A.t.gfirst[u] + A.t.gcount[u] && A.fb[gi]) { f = kFallbackFm; a = kFallbackAm; clean = false; }
                 }
+                clean &= (f != 0.0);
                 fmw[n] = f; amw[n] = a;
             }
+            clean = __all_sync(0xffffffffu, clean);
             __syncwarp();
+            if (clean) {
+                // Fast path: the window lies inside one run of this harmonic.  There fm_current[m] = fs/2pi *
+                // unwrap(ph[m] - ph[m-1]) (functions.py:375), so the running sum telescopes and
+                // E1[n] = exp(j 2 pi (S[n] - S[N]) / fs) = z[n] conj(z[N]) with z = exp(j ph_recon), the phasor track the
+                // interpolation stage wrote: one complex product instead of the gap scan, the running sum and a
+                // sincos per sample (the two forms differ by the rounding of the reference's own running sum, ~1e-14 rad).
+                const double* zck = A.zc_cur + (int64_t)k * A.t.T + us + (cl - N);
+                const double* zsk = A.zs_cur + (int64_t)k * A.t.T + us + (cl - N);
+                double s_lo = 0.0;                           // S[N-1] = sum of fm over the first N samples (for n = L-1 below)
+                for (int n = lane; n < N; n += 32) s_lo += fmw[n];
+                s_lo = warp_sum(s_lo);
+                s_lo = __shfl_sync(0xffffffffu, s_lo, 0);
+                const double fmid = fmw[N], aden = amw[N] + kAmEps;
+                const double zcc = zck[N], zsc = zsk[N];
+                __syncwarp();
+                for (int n = lane; n < L; n += 32) {
+                    const double nc = (double)(n - N), wn = w[n], v = ws[n];
+                    const double c1 = zck[n], s1 = zsk[n];
+                    const double cs = c1 * zcc + s1 * zsc, sn = s1 * zcc - c1 * zsc;
+                    const double r = (kAmEps + amw[n]) / aden;
+                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                    pr[n] = xr; pi[n] = xi;
+                    cp.add(xr, xi, nc, wn, v);
+                    fmw[n] = cs; ni[n] = sn;
+                }
+                __syncwarp();
+                double rs, rc;
+                sincos((kTwoPi * fmid) / fs, &rs, &rc);      // rho = exp(j 2 pi (S[N] - S[N-1]) / fs), S[N] - S[N-1] = fm[N]
+                for (int n = lane; n < N; n += 32) {
+                    const int n2 = L - 2 - n;
+                    const double c1 = fmw[n], s1 = ni[n], c2 = fmw[n2], s2 = ni[n2];
+                    {
+                        const double er = c2 * rc - s2 * rs, ei = c2 * rs + s2 * rc;
+                        const double r = (kAmEps + amw[L - 1 - n]) / aden, wn = w[n];
+                        const double xr = (r * er) * wn, xi = (r * ei) * wn;
+                        nr[n] = xr; ni[n] = xi;
+                        cn.add(xr, xi, (double)(n - N), wn, ws[n]);
+                    }
+                    {
+                        const double er = c1 * rc - s1 * rs, ei = c1 * rs + s1 * rc;
+                        const double r = (kAmEps + amw[n + 1]) / aden, wn = w[n2];
+                        const double xr = (r * er) * wn, xi = (r * ei) * wn;
+                        nr[n2] = xr; ni[n2] = xi;
+                        cn.add(xr, xi, (double)(n2 - N), wn, ws[n2]);
+                    }
+                }
+                if (lane == 0) {
+                    double sn, cs;
+                    sincos((kTwoPi * (0.0 - s_lo)) / fs, &sn, &cs);
+                    const double r = (kAmEps + amw[0]) / aden, wn = w[L - 1];
+                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                    nr[L - 1] = xr; ni[L - 1] = xi;
+                    cn.add(xr, xi, (double)N, wn, ws[L - 1]);
+                }
+                cp.reduce(); cn.reduce();
+                if (lane == 0) {
+                    cp.store(it, Mx, Rb, Rd0, Rd1);
+                    cn.store(nz + it, Mx, Rb, Rd0, Rd1);
+                }
+                __syncwarp();
+                continue;
+            }
             // 2. nearest non-zero neighbour on each side (functions.py:253-271)
             int carry = -1;
             for (int base = 0; base < L; base += 32) {
@@ -1197,6 +1264,8 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     A.s = s;
     A.am_cur = cur->am;
     A.fm_cur = cur->fmc;
+    A.zc_cur = cur->zc;
+    A.zs_cur = cur->zs;
     A.k = *knots;
     A.best_am = best_am;
     A.adapt = adapt;

@@ -220,7 +220,7 @@ class Engine:
             if self.pool is not None:
                 return self.pool.get(name, numel, dtype)
             return torch.zeros(numel, dtype=dtype, device=d)
-        self.tr = [buf("tr%d" % i, K * T) for i in range(3)]                 # am, ph, fmc  [Kmax][T]
+        self.tr = [buf("tr%d" % i, K * T) for i in range(5)]                 # am, ph, fmc, cos ph, sin ph  [Kmax][T]
         self.kn = [buf("kn%d" % i, K * G) for i in range(3)] + [buf("kn3", G)]               # am, ph, fm, a0
         self.best = [buf("best%d" % i, K * G) for i in range(3)] + [buf("best3", G)]
         self.fm_fin = buf("fm_fin", K * G)

@@ -97,6 +97,9 @@ typedef struct {
     double* am;    /* am_recon after interpolation == am_current of the next adaptation */
     double* ph;    /* ph_recon                                                          */
     double* fmc;   /* fm_current (Hz)                                                   */
+    double* zc;    /* cos(ph_recon), sin(ph_recon): written by the interpolation stage; */
+    double* zs;    /* inside a run the next adaptation's basis exp(j 2 pi cumsum(fm_current)/fs) */
+                   /* (functions.py:509-516) is the ratio of two of these phasors       */
 } eaqhm_tracks;
 
 /* Per-frame parameters [Kmax][G] (+ a0 [G]) written by the analysis stage. */

@@ -104,7 +104,7 @@ def test_c_abi_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     # field order/sizes of the ctypes mirrors must follow include/eaqhm_b200.h
-    assert ctypes.sizeof(_lib.Tracks) == 24 and ctypes.sizeof(_lib.Knots) == 32
+    assert ctypes.sizeof(_lib.Tracks) == 40 and ctypes.sizeof(_lib.Knots) == 32
     assert _lib.Tables.T.offset == 0 and _lib.Tables.maxlen.offset == 8 and _lib.Tables.G.offset == 16
     assert _lib.Tables.fs.offset == 32 and _lib.Tables.pos.offset == 40 and _lib.Tables.nA.offset == 40 + 17 * 8 and _lib.Tables.flist.offset == 40 + 18 * 8
 
