@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "audio-seconds analysed+resynthesised per second (eaQHM, c2 1-hour 16 kHz AM-FM signal, frame-range shards)"
 UNIT = "audio-s/s"
+GRAM_TRAFFIC_BYTES = 2.54e9  # per k_gram_warp launch, ncu --set full (profiles/r01_ncu_summary_final.md)
 FP64_PEAK_TFLOPS = 36.9     # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl);
                             # MEASURED_PEAKS.json holds no FP64 figure.  DFMA and DMMA share one pipe.
 
@@ -296,21 +297,24 @@ def main():
     useful = useful_flops
     kt = {k: v[0] / args.steps for k, v in prof.items()}
     dom = max(("gram", "chol_solve", "basis"), key=lambda k: kt[k])
-    dom_fl = {"gram": useful["gram"], "chol_solve": useful["chol"], "basis": useful["basis"]}[dom]
-    achieved = dom_fl / (kt[dom] * 1e-3) / 1e12 if kt[dom] > 0 else 0.0
+    # the Gram kernel forms every complex product from THREE real DMMA products (3M: Re = P1 + P2, Im = P3 - P1 + P2)
+    # instead of four, so it executes 9 L M^2 real flops where the conventional count (8 per complex multiply-add,
+    # accumulated on the device by k_active) is 12 L M^2: `achieved` is what the FP64 pipe really ran (useful flops of
+    # the algorithm used), `achieved_conventional` the same time against the conventional count
+    executed = {"gram": 0.75 * useful["gram"], "chol_solve": useful["chol"], "basis": useful["basis"]}
+    conventional = {"gram": useful["gram"], "chol_solve": useful["chol"], "basis": useful["basis"]}
+    achieved = executed[dom] / (kt[dom] * 1e-3) / 1e12 if kt[dom] > 0 else 0.0
+    conv = conventional[dom] / (kt[dom] * 1e-3) / 1e12 if kt[dom] > 0 else 0.0
     roofline = {"bound": "tensor", "pipe": "FP64 (DFMA and DMMA share one pipe on sm_100a)", "kernel": dom,
                 "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                # dram__bytes_read.sum + dram__bytes_write.sum of k_gram_warp, mean of the four launches captured with
+                "achieved_conventional": conv, "frac_conventional": conv / FP64_PEAK_TFLOPS,
+                # dram__bytes_read.sum + dram__bytes_write.sum of k_gram_warp, mean of the launches captured with
                 # `ncu --set full` on this command's default workload (profiles/r01_ncu_summary_final.md); the algorithmic
                 # bytes of the same launches (basis planes read once + normal matrix written once) are 2.3 GB
-                "traffic": (2.54e9 if (dom == "gram" and args.workload == "c2" and args.shard_seconds == 20.0) else None),
+                "traffic": (GRAM_TRAFFIC_BYTES if (dom == "gram" and args.workload == "c2" and args.shard_seconds == 20.0) else None),
                 "peak_source": "measured FP64 burst (tools/fp64_peak.cu, profiles/r01_fp64_peak.jsonl); "
                                "MEASURED_PEAKS.json has no FP64 entry",
-                # the Gram kernel forms every complex product from THREE real DMMA products (3M: Re = P1 + P2,
-                # Im = P3 - P1 + P2) instead of four, so the pipe executes 9 L M^2 of the conventional 12 L M^2 count:
-                # `achieved` uses the conventional (algorithmic) count, `achieved_executed` what the FP64 pipe really ran
-                "achieved_executed": achieved * (0.75 if dom == "gram" else 1.0),
-                "frac_executed": achieved * (0.75 if dom == "gram" else 1.0) / FP64_PEAK_TFLOPS,
+                "whole_step_executed_tflops": (executed["gram"] + executed["chol_solve"] + executed["basis"]) / (ms_dev * 1e-3) / 1e12,
                 "kernel_ms_per_step": kt, "algorithmic_flops_per_step": useful,
                 "all_kernels_frac_of_step": sum(kt.values()) / ms_dev}
 

@@ -247,18 +247,20 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 for (int n = lane; n < N; n += 32) s_lo += fmw[n];
                 s_lo = warp_sum(s_lo);
                 s_lo = __shfl_sync(0xffffffffu, s_lo, 0);
-                const double fmid = fmw[N], aden = amw[N] + kAmEps;
+                const double fmid = fmw[N], aden = amw[N] + kAmEps, ainv = 1.0 / aden;
                 const double zcc = zck[N], zsc = zsk[N];
                 __syncwarp();
+                // amplitude ratio (functions.py:517-518) once per sample, kept in the amplitude buffer for the mirrored
+                // column (multiplied by the reciprocal: one rounding away from the reference's division)
                 for (int n = lane; n < L; n += 32) {
                     const double nc = (double)(n - N), wn = w[n], v = ws[n];
                     const double c1 = zck[n], s1 = zsk[n];
                     const double cs = c1 * zcc + s1 * zsc, sn = s1 * zcc - c1 * zsc;
-                    const double r = (kAmEps + amw[n]) / aden;
+                    const double r = (kAmEps + amw[n]) * ainv;
                     const double xr = (r * cs) * wn, xi = (r * sn) * wn;
                     pr[n] = xr; pi[n] = xi;
                     cp.add(xr, xi, nc, wn, v);
-                    fmw[n] = cs; ni[n] = sn;
+                    fmw[n] = cs; ni[n] = sn; amw[n] = r;
                 }
                 __syncwarp();
                 double rs, rc;
@@ -268,14 +270,14 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                     const double c1 = fmw[n], s1 = ni[n], c2 = fmw[n2], s2 = ni[n2];
                     {
                         const double er = c2 * rc - s2 * rs, ei = c2 * rs + s2 * rc;
-                        const double r = (kAmEps + amw[L - 1 - n]) / aden, wn = w[n];
+                        const double r = amw[L - 1 - n], wn = w[n];
                         const double xr = (r * er) * wn, xi = (r * ei) * wn;
                         nr[n] = xr; ni[n] = xi;
                         cn.add(xr, xi, (double)(n - N), wn, ws[n]);
                     }
                     {
                         const double er = c1 * rc - s1 * rs, ei = c1 * rs + s1 * rc;
-                        const double r = (kAmEps + amw[n + 1]) / aden, wn = w[n2];
+                        const double r = amw[n + 1], wn = w[n2];
                         const double xr = (r * er) * wn, xi = (r * ei) * wn;
                         nr[n2] = xr; ni[n2] = xi;
                         cn.add(xr, xi, (double)(n2 - N), wn, ws[n2]);
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 if (lane == 0) {
                     double sn, cs;
                     sincos((kTwoPi * (0.0 - s_lo)) / fs, &sn, &cs);
-                    const double r = (kAmEps + amw[0]) / aden, wn = w[L - 1];
+                    const double r = amw[0], wn = w[L - 1];
                     const double xr = (r * cs) * wn, xi = (r * sn) * wn;
                     nr[L - 1] = xr; ni[L - 1] = xi;
                     cn.add(xr, xi, (double)N, wn, ws[L - 1]);
