@@ -35,7 +35,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "audio-seconds analysed+resynthesised per second (eaQHM, c2 1-hour 16 kHz AM-FM signal, frame-range shards)"
 UNIT = "audio-s/s"
-GRAM_TRAFFIC_BYTES = 2.54e9  # per k_gram_warp launch, ncu --set full (profiles/r01_ncu_summary_final.md)
+GRAM_TRAFFIC_BYTES = 23.1e9  # dram read+write per k_gram_warp launch: mean of the two launches of adaptation 1
+                             # (38.7 and 7.5 GB; 12,501 and 8,769 frames), ncu --set full, profiles/r01_ncu_summary_final.md
 FP64_PEAK_TFLOPS = 36.9     # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl);
                             # MEASURED_PEAKS.json holds no FP64 figure.  DFMA and DMMA share one pipe.
 
@@ -310,7 +311,8 @@ def main():
                 "achieved_conventional": conv, "frac_conventional": conv / FP64_PEAK_TFLOPS,
                 # dram__bytes_read.sum + dram__bytes_write.sum of k_gram_warp, mean of the launches captured with
                 # `ncu --set full` on this command's default workload (profiles/r01_ncu_summary_final.md); the algorithmic
-                # bytes of the same launches (basis planes read once + normal matrix written once) are 2.3 GB
+                # bytes of the same launches (basis planes read once + normal matrix written once) are 10.4 GB: panels
+                # are re-fetched ~3x from DRAM (L2 hit 59 %), at 15 % DRAM utilisation under a kernel at 86 % of the FP64 pipe
                 "traffic": (GRAM_TRAFFIC_BYTES if (dom == "gram" and args.workload == "c2" and args.shard_seconds == 20.0) else None),
                 "peak_source": "measured FP64 burst (tools/fp64_peak.cu, profiles/r01_fp64_peak.jsonl); "
                                "MEASURED_PEAKS.json has no FP64 entry",

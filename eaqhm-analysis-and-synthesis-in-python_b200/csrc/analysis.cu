@@ -196,10 +196,10 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
             continue;
         }
         const int k = act[it];
-        double* pr = Xr + (size_t)it * A.Lp;
-        double* pi = Xi + (size_t)it * A.Lp;
-        double* nr = Xr + (size_t)(nz + it) * A.Lp;
-        double* ni = Xi + (size_t)(nz + it) * A.Lp;
+        double* __restrict__ pr = Xr + (size_t)it * A.Lp;
+        double* __restrict__ pi = Xi + (size_t)it * A.Lp;
+        double* __restrict__ nr = Xr + (size_t)(nz + it) * A.Lp;
+        double* __restrict__ ni = Xi + (size_t)(nz + it) * A.Lp;
         ColSums cp, cn;
         cp.zero(); cn.zero();
 
@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
         } else {
             // 1. gather the window of fm_current / am_current (functions.py:244-245); column 0 sees the
             //    in-place fallback writes of this and earlier frames (Q6, functions.py:209-210)
-            const double* fmk = A.fm_cur + (int64_t)k * A.t.T + us;
-            const double* amk = A.am_cur + (int64_t)k * A.t.T + us;
+            const double* __restrict__ fmk = A.fm_cur + (int64_t)k * A.t.T + us;
+            const double* __restrict__ amk = A.am_cur + (int64_t)k * A.t.T + us;
             bool clean = A.zc_cur != nullptr && cl - N >= 0;   // no wrapped indices, no zeros, no fallback substitution
+#pragma unroll 4
             for (int n = lane; n < L; n += 32) {
                 int64_t il = cl - N + n;
                 if (il < 0) il += ul;
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 // E1[n] = exp(j 2 pi (S[n] - S[N]) / fs) = z[n] conj(z[N]) with z = exp(j ph_recon), the phasor track the
                 // interpolation stage wrote: one complex product instead of the gap scan, the running sum and a
                 // sincos per sample (the two forms differ by the rounding of the reference's own running sum, ~1e-14 rad).
-                const double* zck = A.zc_cur + (int64_t)k * A.t.T + us + (cl - N);
-                const double* zsk = A.zs_cur + (int64_t)k * A.t.T + us + (cl - N);
+                const double* __restrict__ zck = A.zc_cur + (int64_t)k * A.t.T + us + (cl - N);
+                const double* __restrict__ zsk = A.zs_cur + (int64_t)k * A.t.T + us + (cl - N);
                 double s_lo = 0.0;                           // S[N-1] = sum of fm over the first N samples (for n = L-1 below)
                 for (int n = lane; n < N; n += 32) s_lo += fmw[n];
                 s_lo = warp_sum(s_lo);
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 __syncwarp();
                 // amplitude ratio (functions.py:517-518) once per sample, kept in the amplitude buffer for the mirrored
                 // column (multiplied by the reciprocal: one rounding away from the reference's division)
+#pragma unroll 4
                 for (int n = lane; n < L; n += 32) {
                     const double nc = (double)(n - N), wn = w[n], v = ws[n];
                     const double c1 = zck[n], s1 = zsk[n];
