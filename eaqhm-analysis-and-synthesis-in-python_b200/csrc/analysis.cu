@@ -33,7 +33,27 @@ struct AnaArgs {
     double2* x;                     // [chunk][Pmax]
     int32_t* status;
     double* flop_stats;             // [3] += algorithmic flops of the Gram / Cholesky / basis+rhs (may be null)
+    int32_t a0_real;                // adaptation 0 solved as two real systems (k_a0_build_real, k_chol_real)
+    int32_t store_X;                // k_basis<false> writes the basis planes (only the dense-Gram path reads them)
 };
+
+// Real even / odd systems of adaptation 0 inside a frame's scratch matrix (see k_a0_build_real)
+struct A0Real {
+    int M, Mp;                      // unknowns per system (2K+1), row pitch in doubles
+    double* sys[2];                 // augmented matrices [M+1][Mp] (row M = right-hand side)
+    double* sol[2];                 // solutions [M]
+};
+__device__ __forceinline__ A0Real a0_real_layout(double2* RF, int Mx) {
+    A0Real r;
+    r.M = Mx + 1;
+    r.Mp = (r.M + 15) & ~15;
+    double* base = reinterpret_cast<double*>(RF);
+    r.sys[0] = base;
+    r.sys[1] = base + (size_t)(r.M + 1) * r.Mp;
+    r.sol[0] = base + (size_t)2 * (r.M + 1) * r.Mp;
+    r.sol[1] = r.sol[0] + r.Mp;
+    return r;
+}
 
 // ---------------------------------------------------------------------------------------
 // fallback flags over ALL analysed frames (functions.py:204-210, quirk Q6): a frame whose
@@ -93,7 +113,8 @@ __global__ void k_active(AnaArgs A) {
         if (A.flop_stats) {   // structure-aware minimum work of this frame
             const double M = 2.0 * count + 1.0, L = 2.0 * A.t.N[g] + 1.0, P = 2.0 * M;
             if (A.adapt > 0) atomicAdd(&A.flop_stats[0], 12.0 * L * M * M);   // adaptation 0 uses the Toeplitz tables
-            atomicAdd(&A.flop_stats[1], (4.0 / 3.0) * P * P * P + 8.0 * P * P);
+            if (A.a0_real) atomicAdd(&A.flop_stats[1], 2.0 * ((1.0 / 3.0) * M * M * M + 2.0 * M * M));   // two real systems
+            else atomicAdd(&A.flop_stats[1], (4.0 / 3.0) * P * P * P + 8.0 * P * P);
             atomicAdd(&A.flop_stats[2], 16.0 * L * M);
         }
     }
@@ -212,7 +233,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 double sn, cs;
                 sincos(t, &sn, &cs);
                 const double wn = w[n], xr = cs * wn, xi = sn * wn, v = ws[n];
-                pr[n] = xr; pi[n] = xi; nr[n] = xr; ni[n] = -xi;
+                if (A.store_X) { pr[n] = xr; pi[n] = xi; nr[n] = xr; ni[n] = -xi; }
                 cp.add(xr, xi, nc, wn, v);
                 cn.add(xr, -xi, nc, wn, v);
             }
@@ -1138,6 +1159,253 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
 }
 
 // ---------------------------------------------------------------------------------------
+// Adaptation 0 in real arithmetic.  The basis of iqhmLS_complexamps (functions.py:453-455) is exp(j h theta n) and
+// n exp(j h theta n), h = -K..K, under a symmetric window on the symmetric sample range n = -N..N, and the signal is real.
+// The minimiser is conjugate symmetric (a_-h = conj a_h), so the model is
+//     sum_k alpha_k cos(k theta n) + gamma_k sin(k theta n) + beta_k n cos(k theta n) + delta_k n sin(k theta n)
+// with a_k = (alpha_k - j gamma_k) / 2, b_k = (beta_k - j delta_k) / 2 (k >= 1), a_0 = alpha_0, b_0 = beta_0, and the even
+// functions {cos, n sin} are orthogonal to the odd ones {sin, n cos} under the weight w^2: the 2(2K+1) complex normal
+// equations split into TWO real symmetric positive definite systems of 2K+1 unknowns whose entries are sums and
+// differences of the same three lag tables as the Toeplitz fill:  16 x fewer flops and 4 x fewer bytes than the complex
+// Cholesky of the same least-squares problem.
+//   even: [alpha_0..alpha_K | delta_1..delta_K]    odd: [gamma_1..gamma_K | beta_0..beta_K]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_a0_build_real(AnaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int jl = blockIdx.x;
+    const int g = A.t.alist[A.j0 + jl];
+    const int N = A.t.N[g], L = 2 * N + 1;
+    const int Mx = A.Mcols[jl], K = Mx / 2;
+    double* w2 = reinterpret_cast<double*>(smem_raw);       // [N+1]  w_n^2 for n = 0..N
+    double* T0 = w2 + (A.Lp / 2 + 2);                       // [2K+1]  sum w^2 cos(d theta n)
+    double* T1 = T0 + (A.Mxmax + 1);                        //         sum n w^2 sin(d theta n)
+    double* T2 = T1 + (A.Mxmax + 1);                        //         sum n^2 w^2 cos(d theta n)
+    for (int n = tid; n <= N; n += 256) {
+        const double nn = (double)(2 * n), den = (double)(L - 1);   // numpy.blackman at index N + n
+        const double wn = 0.42 + 0.5 * cos((kPi * nn) / den) + 0.08 * cos(((2.0 * kPi) * nn) / den);
+        w2[n] = wn * wn;
+    }
+    __syncthreads();
+    const double theta = (kTwoPi * A.t.f0[g]) / A.t.fs;
+    for (int d = tid; d <= 2 * K; d += 256) {
+        double rs, rc;
+        sincos((double)d * theta, &rs, &rc);
+        double zr = 1.0, zi = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int n = 1; n <= N; n++) {
+            const double nzr = zr * rc - zi * rs;
+            zi = zr * rs + zi * rc;
+            zr = nzr;
+            const double wn2 = w2[n], nw = (double)n * wn2;
+            t0 = fma(wn2, zr, t0);
+            t1 = fma(nw, zi, t1);
+            t2 = fma((double)n * nw, zr, t2);
+        }
+        T0[d] = w2[0] + 2.0 * t0;
+        T1[d] = 2.0 * t1;
+        T2[d] = 2.0 * t2;
+    }
+    __syncthreads();
+    double2* RFc = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+    const A0Real ar = a0_real_layout(RFc, Mx);
+    const int M = ar.M, Mp = ar.Mp;
+    auto S1 = [&](int d) { return d < 0 ? -T1[-d] : T1[d]; };
+    for (int e = tid; e < M * M; e += 256) {
+        const int p = e / M, q = e - p * M;
+        if (q > p) continue;
+        {   // even: index <= K is cos(k), k = index; index > K is n sin(k), k = index - K
+            const bool pc = p <= K, qc = q <= K;
+            const int kp = pc ? p : p - K, kq = qc ? q : q - K;
+            const int dm = kp > kq ? kp - kq : kq - kp;
+            double v;
+            if (pc && qc) v = 0.5 * (T0[dm] + T0[kp + kq]);
+            else if (!pc && !qc) v = 0.5 * (T2[dm] - T2[kp + kq]);
+            else v = 0.5 * (S1(kp + kq) + S1(kp - kq));            // p = n sin(kp), q = cos(kq)  (q <= p: q is the cosine)
+            ar.sys[0][(size_t)p * Mp + q] = v;
+        }
+        {   // odd: index < K is sin(k), k = index + 1; index >= K is n cos(k), k = index - K
+            const bool ps = p < K, qs = q < K;
+            const int kp = ps ? p + 1 : p - K, kq = qs ? q + 1 : q - K;
+            const int dm = kp > kq ? kp - kq : kq - kp;
+            double v;
+            if (ps && qs) v = 0.5 * (T0[dm] - T0[kp + kq]);
+            else if (!ps && !qs) v = 0.5 * (T2[dm] + T2[kp + kq]);
+            else v = 0.5 * (S1(kq + kp) + S1(kq - kp));            // p = n cos(kp), q = sin(kq)
+            ar.sys[1][(size_t)p * Mp + q] = v;
+        }
+    }
+    // right-hand sides from the sums k_basis<false> left in row P (and the DC entries) of the complex layout:
+    // Rb[c] = (sum w^2 s cos, sum w^2 s sin), Rb[Mx + c] = the same with the extra factor n, column c <-> harmonic c + 1
+    const int P = 2 * Mx + 2;
+    const double2* Rb = RFc + (size_t)P * A.Pp;
+    double* be = ar.sys[0] + (size_t)M * Mp;
+    double* bo = ar.sys[1] + (size_t)M * Mp;
+    for (int i = tid; i < M; i += 256) {
+        be[i] = i == 0 ? Rb[2 * Mx].x : (i <= K ? Rb[i - 1].x : Rb[Mx + i - K - 1].y);
+        bo[i] = i < K ? Rb[i].y : (i == K ? Rb[2 * Mx + 1].x : Rb[Mx + i - K - 1].x);
+    }
+}
+
+// Real twin of k_chol_solve: left-looking blocked Cholesky (block width 16) of one augmented real system
+// [[R, b],[b^T, .]] per CTA, DMMA block-column update, warp-synchronous diagonal factor, lane-per-row triangular
+// solve, then L^T x = y.  Grid: 2 CTAs per frame (even, odd system).
+template <int kNW>
+__global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_real(AnaArgs A) {
+    constexpr int kThreads = kNW * 32;
+    const int jl = blockIdx.x >> 1, par = blockIdx.x & 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const A0Real ar = a0_real_layout(A.R + (size_t)jl * (A.Pmax + 1) * A.Pp, A.Mcols[jl]);
+    const int P = ar.M, Pp = ar.Mp;
+    double* RF = ar.sys[par];
+    __shared__ double D[kNb][kNb + 1];
+    __shared__ double Tall[kNW][kNb][kNb + 1];
+    __shared__ double red[kThreads / 16][17];
+    __shared__ int bad;
+    extern __shared__ __align__(16) double xsr[];     // [P] solution
+    double (*T)[kNb + 1] = Tall[warp];
+    if (tid == 0) bad = 0;
+    __syncthreads();
+
+    const int nrb = (P + 1 + kNb - 1) / kNb;          // row blocks (the rhs row P is in the last one)
+    const int ncb = (P + kNb - 1) / kNb;              // block columns
+    for (int jbk = 0; jbk < ncb; jbk++) {
+        const int jb = jbk * kNb, nbc = min(kNb, P - jb);
+        int rb = jbk + ((warp - jbk) % kNW + kNW) % kNW;
+        bool d_ready = false;
+        for (; rb < nrb || !d_ready; rb += kNW) {
+            const bool have = rb < nrb;
+            const int i0 = rb * kNb;
+            if (have) {
+                double acc[2][2][2];
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+                if (jb > 0) {
+                    const double* arow[2];
+                    const double* brow[2];
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        arow[s2] = RF + (size_t)min(i0 + s2 * 8 + lr, P) * Pp + lc;
+                        brow[s2] = RF + (size_t)min(jb + s2 * 8 + lr, P) * Pp + lc;
+                    }
+#pragma unroll 4
+                    for (int k0 = 0; k0 < jb; k0 += 4) {
+                        double a[2], b[2];
+#pragma unroll
+                        for (int s2 = 0; s2 < 2; s2++) { a[s2] = -arow[s2][k0]; b[s2] = brow[s2][k0]; }
+#pragma unroll
+                        for (int si = 0; si < 2; si++)
+#pragma unroll
+                            for (int sj = 0; sj < 2; sj++) dmma884(acc[si][sj], a[si], b[sj]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int si = 0; si < 2; si++)
+#pragma unroll
+                    for (int sj = 0; sj < 2; sj++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int r = si * 8 + lr, cidx = sj * 8 + 2 * lc + e, i = i0 + r;
+                            double v = 0.0;
+                            if (i <= P && cidx < nbc && jb + cidx <= i) v = RF[(size_t)i * Pp + jb + cidx] + acc[si][sj][e];
+                            T[r][cidx] = v;
+                        }
+                __syncwarp();
+                if (rb == jbk) {
+                    for (int c = 0; c < nbc; c++) {
+                        const double dd = T[c][c];
+                        if (!(dd > 0.0) && lane == 0) bad = 1;
+                        const double dsq = sqrt(dd), inv = 1.0 / dsq;
+                        __syncwarp();
+                        if (lane == c) T[c][c] = dsq;
+                        else if (lane > c && lane < nbc) T[lane][c] *= inv;
+                        __syncwarp();
+                        for (int e = lane; e < kNb * kNb; e += 32) {
+                            const int r = e >> 4, c2 = e & 15;
+                            if (r > c && r < nbc && c2 > c && c2 <= r) T[r][c2] = fma(-T[r][c], T[c2][c], T[r][c2]);
+                        }
+                        __syncwarp();
+                    }
+                    for (int e = lane; e < kNb * kNb; e += 32) {
+                        const int r = e >> 4, c2 = e & 15;
+                        const double v = (r < nbc && c2 <= r) ? T[r][c2] : 0.0;
+                        D[r][c2] = v;
+                        if (r < nbc && c2 <= r) RF[(size_t)(jb + r) * Pp + jb + c2] = v;
+                    }
+                }
+            }
+            if (!d_ready) {
+                __syncthreads();
+                d_ready = true;
+            }
+            if (have && lane < kNb) {
+                const int i = i0 + lane;
+                if (i <= P && !(rb == jbk && lane < nbc)) {
+                    double W[kNb];
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) W[c] = T[lane][c];
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) {
+                        if (c < nbc) {
+                            double v = W[c];
+#pragma unroll
+                            for (int cc = 0; cc < kNb; cc++) if (cc < c) v = fma(-W[cc], D[c][cc], v);
+                            W[c] = v / D[c][c];
+                        }
+                    }
+                    double* rowp = RF + (size_t)i * Pp + jb;
+#pragma unroll
+                    for (int c = 0; c < kNb; c++) if (c < nbc) rowp[c] = W[c];
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+
+    // back substitution L^T x = y, y = row P of the factor
+    for (int b = ncb - 1; b >= 0; b--) {
+        const int jb = b * kNb, nbc = min(kNb, P - jb);
+        const int c = tid & 15, rr = tid >> 4;
+        for (int e = tid; e < kNb * kNb; e += kThreads) {
+            const int r = e >> 4, c2 = e & 15;
+            D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : 0.0;
+        }
+        double part = 0.0;
+        if (c < nbc) {
+            constexpr int kStride = kThreads / 16;
+            for (int i = jb + nbc + rr; i < P; i += kStride) part = fma(RF[(size_t)i * Pp + jb + c], xsr[i], part);
+        }
+        red[rr][c] = part;
+        const double yq = (tid < nbc) ? RF[(size_t)P * Pp + jb + tid] : 0.0;
+        __syncthreads();
+        if (tid < 32) {
+            double v = 0.0;
+            if (tid < nbc) {
+                v = yq;
+                for (int r2 = 0; r2 < kThreads / 16; r2++) v -= red[r2][tid];
+            }
+            for (int cc = nbc - 1; cc >= 0; cc--) {
+                double xc = 0.0;
+                if (tid == cc) {
+                    xc = v / D[cc][cc];
+                    xsr[jb + cc] = xc;
+                }
+                xc = __shfl_sync(0xffffffffu, xc, cc);
+                if (tid < cc) v = fma(-D[cc][tid], xc, v);
+            }
+        }
+        __syncthreads();
+    }
+    double* xo = ar.sol[par];
+    for (int p = tid; p < P; p += kThreads) xo[p] = xsr[p];
+    if (tid == 0 && bad && A.status) atomicAdd(&A.status[0], 1);
+}
+
+// ---------------------------------------------------------------------------------------
 // frequency mismatch, acceptance test and knot write (functions.py:297-324)
 // ---------------------------------------------------------------------------------------
 __global__ void k_accept(AnaArgs A) {
@@ -1149,18 +1417,24 @@ __global__ void k_accept(AnaArgs A) {
     const double2* x = A.x + (size_t)jl * A.Pmax;
     const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
     const int64_t G = A.t.G;
+    A0Real ar;
+    if (A.a0_real) ar = a0_real_layout(A.R + (size_t)jl * (A.Pmax + 1) * A.Pp, M);
+    // amplitude of the +f column `it`: complex solution, or (alpha_k - j gamma_k) / 2 of the real even / odd systems
+    auto amp_of = [&](int it) {
+        return A.a0_real ? make_double2(0.5 * ar.sol[0][it + 1], -0.5 * ar.sol[1][it]) : x[it];
+    };
     double mx = 0.0;
-    for (int it = lane; it < nz; it += 32) mx = fmax(mx, hypot(x[it].x, x[it].y));
+    for (int it = lane; it < nz; it += 32) { const double2 a = amp_of(it); mx = fmax(mx, hypot(a.x, a.y)); }
     mx = warp_max(mx);
     const double log_max = 20.0 * log10(mx) - 150.0;                       // functions.py:309
     const double f0u = A.adapt == 0 ? A.t.f0[g] : A.t.f0stale[u];         // stale f0 for a >= 1 (Q1)
     const double h = f0u / (double)(A.adapt + 1);                          // functions.py:310
     const bool correct = f0u > A.t.f0min[u];                               // functions.py:321
-    if (lane == 0) A.k.a0[g] = x[2 * M].x;                                 // functions.py:303
+    if (lane == 0) A.k.a0[g] = A.a0_real ? ar.sol[0][0] : x[2 * M].x;      // functions.py:303
     const int64_t c = A.t.pos[g];
     for (int it = lane; it < nz; it += 32) {
         const int k = act[it];
-        const double2 a = x[it];
+        const double2 a = amp_of(it);
         const double mag = hypot(a.x, a.y);
         double df = 0.0;
         if (A.adapt > 0) {
@@ -1297,6 +1571,11 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     }
     CHECK_ARG(smem <= 200 * 1024);
 
+    // experiment knobs (tools only): EAQHM_A0_REAL=0 keeps the complex Toeplitz + Cholesky path at adaptation 0
+    static const bool use_a0_real = !(getenv("EAQHM_A0_REAL") && atoi(getenv("EAQHM_A0_REAL")) == 0);
+    static const bool no_toeplitz = getenv("EAQHM_NO_TOEPLITZ") && atoi(getenv("EAQHM_NO_TOEPLITZ"));
+    A.a0_real = (adapt == 0 && use_a0_real && !no_toeplitz) ? 1 : 0;
+    A.store_X = (adapt == 0 && !no_toeplitz) ? 0 : 1;       // adaptation 0 builds its normal matrix from lag tables
     CUDA_TRY(cudaMemsetAsync(A.fb, 0, tab->G, st));
     if (adapt > 0) {
         A.j0 = 0; A.nf = tab->nA;
@@ -1314,6 +1593,15 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         S.nf = A.nf; S.Mxmax = l.Mxmax; S.dc = 1; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
         static const bool use_toeplitz = !(getenv("EAQHM_NO_TOEPLITZ") && atoi(getenv("EAQHM_NO_TOEPLITZ")));
         const bool toeplitz = adapt == 0 && use_toeplitz;
+        if (A.a0_real) {
+            // adaptation 0 as two real systems per frame (see k_a0_build_real)
+            const size_t tsm = ((size_t)(l.Lp / 2 + 2) + 3 * (size_t)(l.Mxmax + 1)) * 8;
+            CHECK_ARG(tsm <= 48 * 1024);
+            LAUNCH(KC_GRAM, st, k_a0_build_real<<<A.nf, 256, tsm, st>>>(A));
+            LAUNCH(KC_CHOL, st, k_chol_real<2><<<2 * A.nf, 64, (size_t)(l.Mxmax + 2) * 8, st>>>(A));
+            LAUNCH(KC_ACCEPT, st, k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
+            continue;
+        }
         if (toeplitz) {
             const size_t tsm = ((size_t)(l.Lp / 2 + 2) + 3 * (size_t)(l.Mxmax + 1)) * 8;
             CHECK_ARG(tsm <= 48 * 1024);
