@@ -1517,6 +1517,7 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     CHECK_ARG(xs_bytes <= 32 * 1024);
     if (warps == 1) LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a));
     else if (warps == 4) LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a));
+    else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a));
     else LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a));
     return EAQHM_OK;
 }

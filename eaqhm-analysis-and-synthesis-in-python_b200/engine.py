@@ -236,8 +236,12 @@ class Engine:
             if scratch_budget_bytes is None:
                 # big launches amortise the tail of the per-frame kernels (profiles/: 40 GB vs 6 GB = -10 % step time);
                 # stay within a third of what is free so that two engines can coexist
-                free, _ = torch.cuda.mem_get_info(self.device)
-                scratch_budget_bytes = int(min(40 << 30, free // 3))
+                ws = _WORKSPACE.get(str(self.device))
+                if ws is not None and ws.numel() >= (8 << 30):
+                    scratch_budget_bytes = int(ws.numel())      # reuse the process's workspace (no driver query: ~10 ms)
+                else:
+                    free, _ = torch.cuda.mem_get_info(self.device)
+                    scratch_budget_bytes = int(min(40 << 30, free // 3))
             per_frame = self.L.eaqhm_analysis_scratch_bytes(0, 1, self.nnz_max, self.N_max)
             chunk = int(max(1, min(nA, scratch_budget_bytes // max(1, per_frame))))
         self.chunk = int(chunk)

@@ -1,14 +1,20 @@
+"""Where the end-to-end overhead of one bench step goes: engine construction from host arrays, device loop, result read-back."""
 import os, sys, time
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."); sys.path.insert(0, ROOT)
-import numpy as np, torch, bench
-from eaqhm_b200 import engine
-inp = bench.shard_inputs(0, 20.0); utts = [engine.Utterance(**inp)]
-for it in range(4):
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch, bench
+from eaqhm_b200 import longsignal
+inp = bench.long_signal_inputs(20.0)
+for rep in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    e = engine.Engine(utts); torch.cuda.synchronize(); t1 = time.perf_counter()
-    r = e.run_device(); torch.cuda.synchronize(); t2 = time.perf_counter()
-    out = e.results(*r); torch.cuda.synchronize(); t3 = time.perf_counter()
-    print("init %.1f ms  run %.1f ms  results %.1f ms" % ((t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3))
+    e = longsignal.LongSignalEngine(shard_seconds=20.0, **inp)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    out = e.run_device()
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    r = e.results(*out)
+    torch.cuda.synchronize(); t3 = time.perf_counter()
+    del e
+    print("rep %d: construct %.1f ms, device loop %.1f ms, results %.1f ms" % (rep, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
 import cProfile, pstats
-pr = cProfile.Profile(); pr.enable(); e = engine.Engine(utts); torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
+pr = cProfile.Profile(); pr.enable()
+e = longsignal.LongSignalEngine(shard_seconds=20.0, **inp); torch.cuda.synchronize()
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
