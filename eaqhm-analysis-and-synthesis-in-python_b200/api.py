@@ -55,7 +55,7 @@ def make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender="other", ste
                      frame_step=int(frame_step), f0min=float(f0min), Kmax=int(Kmax), det_part=det)
 
 
-STREAM_THRESHOLD_BYTES = 8 << 30     # dense tracks (3 x Kmax x length doubles) above this are streamed shard by shard
+STREAM_THRESHOLD_BYTES = 8 << 30     # dense tracks (5 x Kmax x length doubles) above this are streamed shard by shard
 
 
 def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10,
@@ -66,7 +66,7 @@ def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", ste
     functions.py:159-171) go through the streamed long-signal engine, which gives the same result."""
     u = make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender, step, analysisWindow, fullWaveform, partials)
     limit = STREAM_THRESHOLD_BYTES if stream_threshold_bytes is None else stream_threshold_bytes
-    if 3 * 8 * u.Kmax * len(u.s) > limit:
+    if 5 * 8 * u.Kmax * len(u.s) > limit:
         from .longsignal import LongSignalEngine
         eng = LongSignalEngine(u.s, u.fs, u.f0s, u.voiced5, u.frame_step, u.f0min, u.Kmax, shard_seconds=shard_seconds,
                                det_part=u.det_part, step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods,

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 from .engine import Engine
 from .sharding import partition_round_robin
 
-TRACK_ARRAYS = 3          # am, ph, fmc: the dense per-sample state of a resident batch
+TRACK_ARRAYS = 5          # am, ph, fmc, cos ph, sin ph: the dense per-sample state of a resident batch
 
 
 def utterance_bytes(u):

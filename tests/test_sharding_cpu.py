@@ -21,7 +21,7 @@ def test_partitions_cover_everything_once():
 
 def test_corpus_batches_respect_the_memory_budget():
     sizes, kmaxes = [48000, 48000, 16000, 96000, 48000, 1000], [60, 97, 40, 97, 50, 97]
-    per = lambda n, k: (3 * k + 4) * n * 8
+    per = lambda n, k: (corpus.TRACK_ARRAYS * k + 4) * n * 8
     budget = per(48000 + 48000 + 16000, 97)
     plan = corpus.plan_batches(sizes, kmaxes, budget)
     assert plan[0][0] == 0 and plan[-1][1] == len(sizes) and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
