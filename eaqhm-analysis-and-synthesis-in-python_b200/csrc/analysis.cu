@@ -1511,10 +1511,17 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         if (gram_variant == 3) LAUNCH(KC_GRAM, st, k_gram_warp<false><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
         else LAUNCH(KC_GRAM, st, k_gram_warp<true><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
     }
-    const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
+    // experiment knob (tools only): EAQHM_CHOL_PAD_KB pads the dynamic shared memory to lower the frames per SM
+    static const size_t pad = getenv("EAQHM_CHOL_PAD_KB") ? (size_t)atoi(getenv("EAQHM_CHOL_PAD_KB")) * 1024 : 0;
+    const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2) + pad;
+    static bool chol_attr = false;
+    if (pad && !chol_attr) {
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        chol_attr = true;
+    }
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
-    CHECK_ARG(xs_bytes <= 32 * 1024);
+    CHECK_ARG(xs_bytes - pad <= 32 * 1024);
     if (warps == 1) LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a));
     else if (warps == 4) LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a));
     else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a));
