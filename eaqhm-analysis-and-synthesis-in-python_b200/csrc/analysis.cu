@@ -1567,7 +1567,9 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     A.flop_stats = flop_stats;
     if (tab->nA == 0) return EAQHM_OK;
 
-    int nwb = kBasisWarps;
+    // experiment knob (tools only): EAQHM_BASIS_NWB = warps of a basis CTA that own a column buffer (fewer -> more CTAs per SM)
+    static const int nwb_env = getenv("EAQHM_BASIS_NWB") ? atoi(getenv("EAQHM_BASIS_NWB")) : kBasisWarps;
+    int nwb = nwb_env >= 1 && nwb_env <= kBasisWarps ? nwb_env : kBasisWarps;
     while (nwb > 1 && basis_smem_bytes(l.Lp, nwb) > 200 * 1024) nwb--;
     A.nwb = nwb;
     const size_t smem = basis_smem_bytes(l.Lp, nwb);
