@@ -20,17 +20,19 @@ def _array_by_index(idx, values):
     if len(idx) == 0:
         raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # misc.py:61-62 via functions.py:409
     r = np.zeros(int(idx[-1]) + 1, dtype=object)
-    for i, v in zip(idx, values):
-        r[int(i)] = np.array([v])
+    # one (n,1) array per call; its rows are the one-element arrays (views are ~10x cheaper than np.array([v]))
+    for i, v in zip(idx.tolist(), np.array(values, dtype=float).reshape(-1, 1)):
+        r[i] = v
     return r
 
 
 def pack_det_components(res):
     """functions.py:151,325-329,404-411: list of Deterministic records, one per frame."""
     out = []
-    for i in range(len(res.ti)):
-        d = Deterministic(ti=int(res.ti[i]), isSpeech=bool(res.isSpeech[i]), isVoiced=bool(res.isVoiced[i]))
-        if d.isVoiced:
+    ti, sp, vo = res.ti.tolist(), res.isSpeech.tolist(), res.isVoiced.tolist()
+    for i in range(len(ti)):
+        d = Deterministic(ti=ti[i], isSpeech=sp[i], isVoiced=vo[i])
+        if vo[i]:
             nz = np.flatnonzero(res.am[i])
             d.a0 = res.a0[i]
             d.amplitudes = _array_by_index(nz, res.am[i, nz])
