@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
             //    in-place fallback writes of this and earlier frames (Q6, functions.py:209-210)
             const double* __restrict__ fmk = A.fm_cur + (int64_t)k * A.t.T + us;
             const double* __restrict__ amk = A.am_cur + (int64_t)k * A.t.T + us;
-            bool clean = A.zc_cur != nullptr && cl - N >= 0;   // no wrapped indices, no zeros, no fallback substitution
+            bool clean = A.zc_cur != nullptr && A.zs_cur != nullptr && cl - N >= 0;   // no wrapped indices, no zeros, no fallback substitution
 #pragma unroll 4
             for (int n = lane; n < L; n += 32) {
                 int64_t il = cl - N + n;

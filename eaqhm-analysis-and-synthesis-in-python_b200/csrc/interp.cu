@@ -146,8 +146,9 @@ __global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, 
     double* am = tr.am + (int64_t)k * T;
     double* ph = tr.ph + (int64_t)k * T;
     double* fc = tr.fmc + (int64_t)k * T;
-    double* zc = tr.zc + (int64_t)k * T;         // phasor of the phase track (cos, sin): the next adaptation's
-    double* zs = tr.zs + (int64_t)k * T;         // basis inside a run is a ratio of two of these (k_basis)
+    const bool zz = tr.zc != nullptr && tr.zs != nullptr;   // phasor tracks are optional (NULL: analysis takes its slow path)
+    double* zc = zz ? tr.zc + (int64_t)k * T : nullptr;     // phasor of the phase track (cos, sin): the next adaptation's
+    double* zs = zz ? tr.zs + (int64_t)k * T : nullptr;     // basis inside a run is a ratio of two of these (k_basis)
     auto acc = [&](int d) { const int j = gl + d; return j >= 0 && j < nu && amk[g + d] != 0.0; };
     const double y0 = amk[g];
     const bool a0 = y0 != 0.0, has_prev = a0 && acc(-1), has_next = a0 && acc(1);
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, 
         // (functions.py:350-358 never interpolates it); the last knot of a run is written by its
         // predecessor's thread.
         for (int s = has_prev ? 1 : 0; s < own; s++) {
-            am[x0 + s] = 0.0; ph[x0 + s] = 0.0; fc[x0 + s] = 0.0; zc[x0 + s] = 0.0; zs[x0 + s] = 0.0;
+            am[x0 + s] = 0.0; ph[x0 + s] = 0.0; fc[x0 + s] = 0.0;
+            if (zz) { zc[x0 + s] = 0.0; zs[x0 + s] = 0.0; }
         }
         if (a0 && !has_prev) { am[x0] = y0; ph[x0] = phk[g]; }
         if (!has_prev) fm_fin[(int64_t)k * G + g] = a0 ? fmk[g] : 0.0;
@@ -219,9 +221,11 @@ __global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, 
         if (s < D) {
             am[x0 + s] = (s == 0) ? y0 : slope * (double)s + y0;
             ph[x0 + s] = p;
-            double sn, cs;
-            sincos(p, &sn, &cs);
-            zc[x0 + s] = cs; zs[x0 + s] = sn;
+            if (zz) {
+                double sn, cs;
+                sincos(p, &sn, &cs);
+                zc[x0 + s] = cs; zs[x0 + s] = sn;
+            }
             pprev = p;
         } else {
             double pnext;
@@ -229,9 +233,11 @@ __global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, 
                 pnext = p;
                 am[x0 + D] = y1;
                 ph[x0 + D] = p;
-                double sn, cs;
-                sincos(p, &sn, &cs);
-                zc[x0 + D] = cs; zs[x0 + D] = sn;
+                if (zz) {
+                    double sn, cs;
+                    sincos(p, &sn, &cs);
+                    zc[x0 + D] = cs; zs[x0 + D] = sn;
+                }
                 fm_fin[(int64_t)k * G + g + 1] = fv;
             } else {
                 // the next segment restarts from the measured phase (functions.py:562,571)
@@ -285,7 +291,7 @@ extern "C" int64_t eaqhm_interp_work_bytes(int32_t G, int32_t Kmax) {
 extern "C" int eaqhm_interpolate(const eaqhm_tables* tab, const eaqhm_knots* knots, const eaqhm_tracks* out,
                                  double* fm_fin, double* a0mom, void* work, int64_t work_bytes, void* stream) {
     CHECK_ARG(tab && knots && out && fm_fin && a0mom && work);
-    CHECK_ARG(out->am && out->ph && out->fmc && out->zc && out->zs);
+    CHECK_ARG(out->am && out->ph && out->fmc && (out->zc == nullptr) == (out->zs == nullptr));
     CHECK_ARG(work_bytes >= eaqhm_interp_work_bytes(tab->G, tab->Kmax));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_cp_table();

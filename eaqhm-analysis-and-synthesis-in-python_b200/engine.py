@@ -132,7 +132,7 @@ class Engine:
 
     def __init__(self, utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32,
                  device="cuda", chunk=None, scratch_budget_bytes=None, frame_tables=None,
-                 pool=None):
+                 pool=None, phasor_tracks=True):
         if not torch.cuda.is_available():
             raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
         self.L = _lib.lib()
@@ -220,7 +220,9 @@ class Engine:
             if self.pool is not None:
                 return self.pool.get(name, numel, dtype)
             return torch.zeros(numel, dtype=dtype, device=d)
-        self.tr = [buf("tr%d" % i, K * T) for i in range(5)]                 # am, ph, fmc, cos ph, sin ph  [Kmax][T]
+        # am, ph, fmc [Kmax][T] and, unless switched off (then the analysis always forms the reference's running sum
+        # itself: 40 % less track memory, slower basis), the phasor tracks cos ph, sin ph
+        self.tr = [buf("tr%d" % i, K * T) for i in range(5 if phasor_tracks else 3)]
         self.kn = [buf("kn%d" % i, K * G) for i in range(3)] + [buf("kn3", G)]               # am, ph, fm, a0
         self.best = [buf("best%d" % i, K * G) for i in range(3)] + [buf("best3", G)]
         self.fm_fin = buf("fm_fin", K * G)
@@ -259,7 +261,7 @@ class Engine:
         t.nA = 0
         t.flist, t.nF = None, 0
         self.best_am_ptr = None         # default: this engine's own snapshot (Q10); a streamed signal points it at its store
-        self.c_tr = _lib.Tracks(*[x.data_ptr() for x in self.tr])
+        self.c_tr = _lib.Tracks(*([x.data_ptr() for x in self.tr] + [None] * (5 - len(self.tr))))
         self.c_kn = _lib.Knots(*[x.data_ptr() for x in self.kn])
         self.c_best = _lib.Knots(*[x.data_ptr() for x in self.best])
         self.h2d_bytes = _h2d_counter[0]

@@ -99,7 +99,8 @@ typedef struct {
     double* fmc;   /* fm_current (Hz)                                                   */
     double* zc;    /* cos(ph_recon), sin(ph_recon): written by the interpolation stage; */
     double* zs;    /* inside a run the next adaptation's basis exp(j 2 pi cumsum(fm_current)/fs) */
-                   /* (functions.py:509-516) is the ratio of two of these phasors       */
+                   /* (functions.py:509-516) is the ratio of two of these phasors.  Both may be  */
+                   /* NULL: the analysis then always forms the running sum itself        */
 } eaqhm_tracks;
 
 /* Per-frame parameters [Kmax][G] (+ a0 [G]) written by the analysis stage. */

@@ -265,6 +265,22 @@ def test_chunked_analysis_equals_unchunked_bitwise():
     assert a.SRER == b.SRER and (a.s_recon == b.s_recon).all() and (a.am == b.am).all()
 
 
+def test_basis_fast_path_equals_running_sum_path():
+    """The phasor-track fast path of the adaptive basis (k_basis) against the reference-shaped path (gap scan, running
+    sum, sincos per sample), selected by passing no phasor tracks through the C ABI: same support, SRER and waveform far
+    inside the parity tolerances (the two differ by the rounding of the running sum only)."""
+    from eaqhm_b200 import synthetic
+    inp = synth_inputs(synthetic.config_c2(duration=1.5), maxAdpt=4)
+    fast, slow = run_cuda(inp), run_cuda(inp, phasor_tracks=False)
+    assert len(fast.SRER) == len(slow.SRER) >= 3
+    assert np.abs(np.array(fast.SRER) - np.array(slow.SRER)).max() <= 1e-9
+    assert np.abs(fast.s_recon - slow.s_recon).max() <= 1e-10
+    assert ((fast.am != 0) == (slow.am != 0)).all()
+    v = fast.isVoiced
+    fmax = np.abs(slow.am[v]).max(axis=1, keepdims=True)
+    assert (np.abs(fast.am[v] - slow.am[v]) / fmax).max() <= 1e-10
+
+
 def test_rerun_is_deterministic():
     from eaqhm_b200 import synthetic
     inp = synth_inputs(synthetic.config_c3(4, duration=0.3), maxAdpt=2)
