@@ -1,5 +1,7 @@
 // Stage B of one eaQHM adaptation: interpolation of the per-frame parameters between frame
 // centres (reference: functions.py:337-383 and phase_integr_interpolation :537-575).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -250,6 +252,145 @@ __global__ void __launch_bounds__(128) k_interp(eaqhm_tables t, eaqhm_knots kn, 
     }
 }
 
+// Coalesced variant: a half-warp (16 lanes) per (harmonic k, frame g), lane = sample inside the frame, so that the
+// five tracks are written 128 contiguous bytes at a time (k_interp above writes one sample per lane 15 samples apart).
+// The running sums of functions.py:561,569 become half-warp scans (same terms, pairwise instead of sequential order:
+// ~1e-16 relative); everything else is the arithmetic of k_interp.
+__device__ __forceinline__ double hw_sum(double v, unsigned mask) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+__device__ __forceinline__ double hw_scan(double v, int sl, unsigned mask) {   // inclusive prefix sum over the half-warp
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const double t = __shfl_up_sync(mask, v, o, 16);
+        if (sl >= o) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_interp_hw(eaqhm_tables t, eaqhm_knots kn, eaqhm_tracks tr, const double* mom,
+                                                  double* fm_fin) {
+    const int sl = threadIdx.x & 15;
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int k = blockIdx.y;
+    if (g >= t.G) return;
+    const int u = t.utt[g];
+    if (!t.active[u]) return;
+    const int64_t G = t.G, T = t.T;
+    const int64_t x0 = t.pos[g];
+    const int own = t.own[g];
+    const int gl = g - t.gfirst[u], nu = t.gcount[u];
+    const double* amk = kn.am + (int64_t)k * G;
+    const double* fmk = kn.fm + (int64_t)k * G;
+    const double* phk = kn.ph + (int64_t)k * G;
+    double* am = tr.am + (int64_t)k * T;
+    double* ph = tr.ph + (int64_t)k * T;
+    double* fc = tr.fmc + (int64_t)k * T;
+    const bool zz = tr.zc != nullptr && tr.zs != nullptr;
+    double* zc = zz ? tr.zc + (int64_t)k * T : nullptr;
+    double* zs = zz ? tr.zs + (int64_t)k * T : nullptr;
+    auto acc = [&](int d) { const int j = gl + d; return j >= 0 && j < nu && amk[g + d] != 0.0; };
+    const double y0 = amk[g];
+    const bool a0 = y0 != 0.0, has_prev = a0 && acc(-1), has_next = a0 && acc(1);
+
+    if (!has_next) {
+        for (int s = sl; s < own; s += 16) {
+            if (s == 0 && has_prev) continue;              // the last knot of a run was written by its predecessor
+            const bool imp = s == 0 && a0;                 // isolated accepted frame: one-sample impulse
+            am[x0 + s] = imp ? y0 : 0.0; ph[x0 + s] = imp ? phk[g] : 0.0; fc[x0 + s] = 0.0;
+            if (zz) { zc[x0 + s] = 0.0; zs[x0 + s] = 0.0; }
+        }
+        if (sl == 0 && !has_prev) fm_fin[(int64_t)k * G + g] = a0 ? fmk[g] : 0.0;
+        return;
+    }
+
+    const int D = t.step;
+    const double h = (double)D;
+    const double y1 = amk[g + 1];
+    const bool next_last = !acc(2);
+    const int nback = has_prev ? (acc(-2) ? 2 : 1) : 0;
+    const int nfwd = next_last ? 0 : (acc(3) ? 2 : 1);
+    const bool shortrun = (nback + 2 + nfwd) < 4;
+    double LX[4], LY[4];
+    const int64_t xoff = t.xoff[u];
+    const double xl0 = (double)(x0 - t.ustart[u] + xoff);
+    if (shortrun) {
+        const int gs = g - nback;
+        const int nrun = nback + 2 + nfwd;
+        const int64_t gu = t.gfirst[u];
+        int c = 0;
+        for (int e = 0; e < 4 - nrun; e++) { LX[c] = (double)(e * D); LY[c] = xoff == 0 ? fmk[gu + e] : 0.0; c++; }
+        for (int e = 0; e < nrun; e++) { LX[c] = (double)(t.pos[gs + e] - t.ustart[u] + xoff); LY[c] = fmk[gs + e]; c++; }
+    }
+    const double f0k = fmk[g], f1k = fmk[g + 1];
+    const double m0 = shortrun ? 0.0 : mom[(int64_t)k * G + g], m1 = shortrun ? 0.0 : mom[(int64_t)k * G + g + 1];
+    auto fm_at = [&](int s) {
+        return shortrun ? lagrange4(LX, LY, xl0 + (double)s) : spline_eval(f0k, f1k, m0, m1, h, (double)s);
+    };
+    const double wscale = kTwoPi / t.fs, fscale = t.fs / kTwoPi;
+    const int nblk = (D + 1 + 15) / 16;                    // samples s = 0..D in blocks of 16 lanes
+    // pass 1: end value of the running phase sum (functions.py:561-562)
+    double csum = 0.0, fv0 = 0.0;
+    for (int b = 0; b < nblk; b++) {
+        const int s = b * 16 + sl;
+        const double fv = s <= D ? fm_at(s) : 0.0;
+        if (b == 0) fv0 = fv;
+        csum += s <= D ? wscale * fv : 0.0;
+    }
+    csum = hw_sum(csum, mask);
+    const double w0 = wscale * __shfl_sync(mask, fv0, 0, 16);
+    const double ph0 = phk[g], ph1 = phk[g + 1];
+    const double shift = ph0 - w0;
+    const double pend = csum + shift;
+    const double Mr = rint((pend - ph1) / kTwoPi);                              // functions.py:564
+    const double er = kPi * ((pend - ph1) - kTwoPi * Mr) / (double)(2 * D);    // functions.py:565
+    const double slope = (y1 - y0) / h;
+    // pass 2: corrected phase, amplitude, new instantaneous frequency (functions.py:364,566-571,375)
+    double c_carry = 0.0, e_carry = 0.0, p_carry = 0.0;
+    for (int b = 0; b < nblk; b++) {
+        const int s = b * 16 + sl;
+        const bool in = s <= D;
+        const double fv = (nblk == 1) ? fv0 : (in ? fm_at(s) : 0.0);
+        const double c2 = hw_scan(in ? wscale * fv : 0.0, sl, mask) + c_carry;
+        const double e2 = hw_scan(in ? sin((kPi * (double)s) / h) * er : 0.0, sl, mask) + e_carry;
+        const double p = (c2 + shift) - e2;
+        double pprev = __shfl_up_sync(mask, p, 1, 16);
+        if (sl == 0) pprev = p_carry;
+        c_carry = __shfl_sync(mask, c2, 15, 16);
+        e_carry = __shfl_sync(mask, e2, 15, 16);
+        p_carry = __shfl_sync(mask, p, 15, 16);
+        if (!in) continue;
+        if (s == 0) {
+            if (!has_prev) fc[x0] = fv;                                        // functions.py:375 first sample
+            fm_fin[(int64_t)k * G + g] = fv;
+        } else if (s < D) {
+            fc[x0 + s] = fscale * unwrap_diff(p - pprev);
+        }
+        if (s < D) {
+            am[x0 + s] = (s == 0) ? y0 : slope * (double)s + y0;
+            ph[x0 + s] = p;
+            if (zz) { double sn, cs; sincos(p, &sn, &cs); zc[x0 + s] = cs; zs[x0 + s] = sn; }
+        } else {
+            double pnext;
+            if (next_last) {
+                pnext = p;
+                am[x0 + D] = y1;
+                ph[x0 + D] = p;
+                if (zz) { double sn, cs; sincos(p, &sn, &cs); zc[x0 + D] = cs; zs[x0 + D] = sn; }
+                fm_fin[(int64_t)k * G + g + 1] = fv;
+            } else {
+                const double fn0 = shortrun ? fv : spline_eval(f1k, 0.0, m1, 0.0, h, 0.0);
+                const double wn0 = wscale * fn0;
+                pnext = wn0 + (ph1 - wn0);
+            }
+            fc[x0 + D] = fscale * unwrap_diff(pnext - pprev);
+        }
+    }
+}
+
 // dense-input version of the phase integration for the helper seam (functions.py:537-575)
 __global__ void k_phase_integr_dense(const double* fm, const double* phc, const int64_t* idx, int n, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,8 +442,15 @@ extern "C" int eaqhm_interpolate(const eaqhm_tables* tab, const eaqhm_knots* kno
     dim3 gm((nchunk + 127) / 128, tab->Kmax);
     LAUNCH(KC_RUN_MOMENTS, st, k_run_moments<<<gm, 128, 0, st>>>(*tab, *knots, mom));
     LAUNCH(KC_A0_MOMENTS, st, k_a0_moments<<<(nchunk + 127) / 128, 128, 0, st>>>(*tab, knots->a0, a0mom));
-    dim3 grid((tab->G + 127) / 128, tab->Kmax);
-    LAUNCH(KC_INTERP, st, k_interp<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin));
+    // experiment knob (tools only): EAQHM_INTERP_VARIANT=1 selects the thread-per-frame kernel
+    static const int variant = getenv("EAQHM_INTERP_VARIANT") ? atoi(getenv("EAQHM_INTERP_VARIANT")) : 0;
+    if (variant == 1) {
+        dim3 grid((tab->G + 127) / 128, tab->Kmax);
+        LAUNCH(KC_INTERP, st, k_interp<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin));
+    } else {
+        dim3 grid((tab->G + 7) / 8, tab->Kmax);           // 8 half-warps (frames) per CTA
+        LAUNCH(KC_INTERP, st, k_interp_hw<<<grid, 128, 0, st>>>(*tab, *knots, *out, mom, fm_fin));
+    }
     return EAQHM_OK;
 }
 
