@@ -775,6 +775,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
             const double* bi_s = st + ((diag ? 0 : 1) * 2 + 1) * 16 * kG2P + lr * kG2P + lc;
 #pragma unroll
             for (int kk = 0; kk < kG2K; kk += 4) {
+                if (c * kG2K + kk >= L) break;                 // k-steps past the window end of the last stage
                 const double nc = (double)(c * kG2K + kk + lc - N), nc2 = nc * nc;
                 double ar[2], ai[2], ax[2], br[2][3], bi[2][3], bx[2][3];
 #pragma unroll
