@@ -269,14 +269,20 @@ class LongSignalEngine:
         views = [_to_host(self.s_best, "ls")] + [_to_host(x[o0:o1], "lk%d" % i) for i, x in enumerate(self.best)]
         status = self.pool.get("status", 2, torch.int32).cpu().numpy()
         n = self.F_hi - self.F_lo
-        s_recon = np.zeros(full.length)
-        s_recon[self.R_lo:self.R_hi] = views[0].numpy()
-        am, fm, ph = (np.zeros((full.No_ti, K)) for _ in range(3))
-        a0 = np.zeros(full.No_ti)
-        am[self.F_lo:self.F_hi] = views[1].numpy().reshape(n, K)
-        ph[self.F_lo:self.F_hi] = views[2].numpy().reshape(n, K)
-        fm[self.F_lo:self.F_hi] = views[3].numpy().reshape(n, K)
-        a0[self.F_lo:self.F_hi] = views[4].numpy()
+        if self.world == 1:
+            # the rank owns the whole signal: one copy out of the pinned staging buffers
+            s_recon = views[0].numpy().copy()
+            am, ph, fm = (views[i].numpy().reshape(n, K).copy() for i in (1, 2, 3))
+            a0 = views[4].numpy().copy()
+        else:
+            s_recon = np.zeros(full.length)
+            s_recon[self.R_lo:self.R_hi] = views[0].numpy()
+            am, fm, ph = (np.zeros((full.No_ti, K)) for _ in range(3))
+            a0 = np.zeros(full.No_ti)
+            am[self.F_lo:self.F_hi] = views[1].numpy().reshape(n, K)
+            ph[self.F_lo:self.F_hi] = views[2].numpy().reshape(n, K)
+            fm[self.F_lo:self.F_hi] = views[3].numpy().reshape(n, K)
+            a0[self.F_lo:self.F_hi] = views[4].numpy()
         self.d2h_bytes += (self.R_hi - self.R_lo) * 8 + n * (3 * K + 1) * 8
         return Result(s_recon=s_recon, SRER=list(SRER), ti=full.ti0.copy(), isSpeech=full.isSpeech.copy(),
                       isVoiced=full.analysed.copy(), a0=a0, am=am, fm=fm, ph=ph, n_adapt_best=int(best_a),
