@@ -243,17 +243,32 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
             const double* __restrict__ fmk = A.fm_cur + (int64_t)k * A.t.T + us;
             const double* __restrict__ amk = A.am_cur + (int64_t)k * A.t.T + us;
             bool clean = A.zc_cur != nullptr && A.zs_cur != nullptr && cl - N >= 0;   // no wrapped indices, no zeros, no fallback substitution
-#pragma unroll 4
-            for (int n = lane; n < L; n += 32) {
-                int64_t il = cl - N + n;
-                if (il < 0) il += ul;
-                double f = fmk[il], a = amk[il];
-                if (k == 0 && (il % A.t.step) == 0) {
-                    const int64_t gi = A.t.gfirst[u] + il / A.t.step;
-                    if (gi <= g && gi < A.t.gfirst[u] + A.t.gcount[u] && A.fb[gi]) { f = kFallbackFm; a = kFallbackAm; clean = false; }
+            // four samples per lane and trip: the eight loads are issued before the first use (the kernel is bound by
+            // the latency of these gathers: ncu source view, profiles/r01_ncu_summary_final.md)
+            for (int n0 = lane; n0 < L; n0 += 128) {
+                double fq[4], aq[4];
+                int64_t ilq[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int n = n0 + 32 * q;
+                    int64_t il = cl - N + (n < L ? n : 0);
+                    if (il < 0) il += ul;
+                    ilq[q] = il;
+                    fq[q] = fmk[il]; aq[q] = amk[il];
                 }
-                clean &= (f != 0.0);
-                fmw[n] = f; amw[n] = a;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int n = n0 + 32 * q;
+                    if (n >= L) break;
+                    double f = fq[q], a = aq[q];
+                    const int64_t il = ilq[q];
+                    if (k == 0 && (il % A.t.step) == 0) {
+                        const int64_t gi = A.t.gfirst[u] + il / A.t.step;
+                        if (gi <= g && gi < A.t.gfirst[u] + A.t.gcount[u] && A.fb[gi]) { f = kFallbackFm; a = kFallbackAm; clean = false; }
+                    }
+                    clean &= (f != 0.0);
+                    fmw[n] = f; amw[n] = a;
+                }
             }
             clean = __all_sync(0xffffffffu, clean);
             __syncwarp();
@@ -274,16 +289,26 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
                 __syncwarp();
                 // amplitude ratio (functions.py:517-518) once per sample, kept in the amplitude buffer for the mirrored
                 // column (multiplied by the reciprocal: one rounding away from the reference's division)
-#pragma unroll 4
-                for (int n = lane; n < L; n += 32) {
-                    const double nc = (double)(n - N), wn = w[n], v = ws[n];
-                    const double c1 = zck[n], s1 = zsk[n];
-                    const double cs = c1 * zcc + s1 * zsc, sn = s1 * zcc - c1 * zsc;
-                    const double r = (kAmEps + amw[n]) * ainv;
-                    const double xr = (r * cs) * wn, xi = (r * sn) * wn;
-                    pr[n] = xr; pi[n] = xi;
-                    cp.add(xr, xi, nc, wn, v);
-                    fmw[n] = cs; ni[n] = sn; amw[n] = r;
+                for (int n0 = lane; n0 < L; n0 += 128) {
+                    double cq[4], sq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int n = n0 + 32 * q, ns = n < L ? n : 0;
+                        cq[q] = zck[ns]; sq[q] = zsk[ns];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int n = n0 + 32 * q;
+                        if (n >= L) break;
+                        const double nc = (double)(n - N), wn = w[n], v = ws[n];
+                        const double c1 = cq[q], s1 = sq[q];
+                        const double cs = c1 * zcc + s1 * zsc, sn = s1 * zcc - c1 * zsc;
+                        const double r = (kAmEps + amw[n]) * ainv;
+                        const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                        pr[n] = xr; pi[n] = xi;
+                        cp.add(xr, xi, nc, wn, v);
+                        fmw[n] = cs; ni[n] = sn; amw[n] = r;
+                    }
                 }
                 __syncwarp();
                 double rs, rc;
