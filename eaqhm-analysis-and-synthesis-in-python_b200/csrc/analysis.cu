@@ -1003,11 +1003,10 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
                         arow[s2] = RF + (size_t)min(i0 + s2 * 8 + lr, P) * Pp + lc;
                         brow[s2] = RF + (size_t)min(jb + s2 * 8 + lr, P) * Pp + lc;
                     }
-#pragma unroll 4
-                    for (int k0 = 0; k0 < jb; k0 += 4) {
-                        double2 a[2], b[2];
-#pragma unroll
-                        for (int s2 = 0; s2 < 2; s2++) { a[s2] = arow[s2][k0]; b[s2] = brow[s2][k0]; }
+                    // Software pipeline in registers: jb is a multiple of 16, i.e. of four k-steps.  Two operand sets of two
+                    // k-steps each; the loads of one set are issued before the 32 DMMAs of the other, so a warp always has
+                    // eight 16-byte loads in flight while it computes (the first DMMA after a load group was the top stall).
+                    auto kstep = [&](const double2 (&a)[2], const double2 (&b)[2]) {
                         if (kChol3M) {
                             double as[2], bd[2];
 #pragma unroll
@@ -1032,6 +1031,20 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
                                     dmma884(wi[si][sj], a[si].x, b[sj].y);
                                 }
                         }
+                    };
+                    double2 pa[2][2], pb[2][2], qa[2][2], qb[2][2];      // [k-step within the set][row half]
+                    auto load2 = [&](double2 (&sa)[2][2], double2 (&sb)[2][2], int k0) {
+#pragma unroll
+                        for (int q = 0; q < 2; q++)
+#pragma unroll
+                            for (int s2 = 0; s2 < 2; s2++) { sa[q][s2] = arow[s2][k0 + 4 * q]; sb[q][s2] = brow[s2][k0 + 4 * q]; }
+                    };
+                    load2(pa, pb, 0);
+                    for (int k0 = 0; k0 < jb; k0 += 16) {
+                        load2(qa, qb, k0 + 8);
+                        kstep(pa[0], pb[0]); kstep(pa[1], pb[1]);
+                        if (k0 + 16 < jb) load2(pa, pb, k0 + 16);
+                        kstep(qa[0], qb[0]); kstep(qa[1], qb[1]);
                     }
                     if (kChol3M) {
 #pragma unroll
