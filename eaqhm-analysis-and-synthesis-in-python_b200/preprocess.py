@@ -189,23 +189,31 @@ def swipep(x, fs, plim, dt=0.001, dlog2p=1.0 / 96.0, dERBs=0.1):
         mu = np.ones(len(j))
         mu[k] = 1 - np.abs(d[j[k]] - (i + 1))
         S[j, :] = S[j, :] + mu[:, None] * Si
-    # parabolic refinement around the strongest candidate of every frame (SWIPE.py:106-131)
+    # parabolic refinement around the strongest candidate of every frame (SWIPE.py:106-131), all frames that share a
+    # winning candidate at once: the parabola through the three strengths (what polyfit(.., 2) returns for three points,
+    # here in Newton form) evaluated by Horner on the fine pitch grid of that candidate
     p = np.full(len(t), np.nan)
     s = np.full(len(t), np.nan)
-    for jj in range(len(t)):
-        col = S[:, jj]
-        s[jj] = col.max(0)
-        i = int(np.argmax(col))
-        if i == 0 or i == len(pc) - 1:
-            p[jj] = pc[0]
-        else:
-            I = np.arange(i - 1, i + 2)
-            tc = 1 / pc[I]
-            ntc = ((tc / tc[1]) - 1) * 2 * np.pi
-            c = np.polyfit(ntc, col[I], 2)
-            ftc = 1 / np.power(2, np.arange(np.log2(pc[I[0]]), np.log2(pc[I[2]]), 0.0013021))
-            nftc = ((ftc / tc[1]) - 1) * 2 * np.pi
-            vals = np.polyval(c, nftc)
-            s[jj] = vals.max(0)
-            p[jj] = 2 ** (np.log2(pc[I[0]]) + (int(np.argmax(vals)) - 1) / 768)
+    best = np.argmax(S, axis=0)
+    s[:] = S[best, np.arange(len(t))]
+    edge = (best == 0) | (best == len(pc) - 1)
+    p[edge] = pc[0]
+    for i in np.unique(best[~edge]):
+        cols = np.flatnonzero(best == i)
+        I = np.arange(i - 1, i + 2)
+        tc = 1 / pc[I]
+        x = ((tc / tc[1]) - 1) * 2 * np.pi
+        y = S[I][:, cols]                                            # (3, frames)
+        d01 = (y[1] - y[0]) / (x[1] - x[0])
+        d12 = (y[2] - y[1]) / (x[2] - x[1])
+        c2 = (d12 - d01) / (x[2] - x[0])
+        c1 = d01 - c2 * (x[0] + x[1])
+        c0 = y[0] - x[0] * (d01 - c2 * x[1])
+        ftc = 1 / np.power(2, np.arange(np.log2(pc[I[0]]), np.log2(pc[I[2]]), 0.0013021))
+        nftc = ((ftc / tc[1]) - 1) * 2 * np.pi
+        vals = (c2[None, :] * nftc[:, None] + c1[None, :]) * nftc[:, None] + c0[None, :]      # Horner, like polyval
+        s[cols] = vals.max(axis=0)
+        km = np.argmax(vals, axis=0)
+        for kk in np.unique(km):                                      # scalar power like SWIPE.py:131 (same last bit)
+            p[cols[km == kk]] = 2 ** (np.log2(pc[I[0]]) + (int(kk) - 1) / 768)
     return np.stack([t, p, s], axis=1)
