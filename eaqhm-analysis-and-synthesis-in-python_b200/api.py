@@ -58,6 +58,7 @@ def make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender="other", ste
 
 
 STREAM_THRESHOLD_BYTES = 8 << 30     # dense tracks (5 x Kmax x length doubles) above this are streamed shard by shard
+MONOLITHIC_LIMIT_BYTES = 100 << 30   # ... unless the signal has wrapping windows and still fits one GPU
 
 
 def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10,
@@ -68,7 +69,14 @@ def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", ste
     functions.py:159-171) go through the streamed long-signal engine, which gives the same result."""
     u = make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender, step, analysisWindow, fullWaveform, partials)
     limit = STREAM_THRESHOLD_BYTES if stream_threshold_bytes is None else stream_threshold_bytes
-    if 5 * 8 * u.Kmax * len(u.s) > limit:
+    stream = 5 * 8 * u.Kmax * len(u.s) > limit
+    if stream:
+        # a window that wraps to the end of the signal (functions.py:196 with a negative start index) is only
+        # reproduced by the monolithic engine: keep such signals there as long as their tracks fit at all
+        ft = host.FrameTables(len(u.s), u.fs, u.f0s, u.voiced5, u.frame_step, u.Kmax, step, pitchPeriods, analysisWindow)
+        if len(ft.wrapping_frames()) and 5 * 8 * u.Kmax * len(u.s) <= MONOLITHIC_LIMIT_BYTES:
+            stream = False
+    if stream:
         from .longsignal import LongSignalEngine
         eng = LongSignalEngine(u.s, u.fs, u.f0s, u.voiced5, u.frame_step, u.f0min, u.Kmax, shard_seconds=shard_seconds,
                                det_part=u.det_part, step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods,
@@ -89,13 +97,18 @@ def analyze_batch(utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindo
 def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', step: int = 15,
                               maxAdpt: int = 10, pitchPeriods: int = 3, analysisWindow: int = 32,
                               fullWaveform: bool = True, fc: int = 0, partials: int = 0,
-                              printPrompts: bool = True, loadingScreen: bool = True, *, f0s=None, frames=None):
+                              printPrompts: bool = True, loadingScreen: bool = True, *, f0s=None, frames=None,
+                              return_tensors: bool = False):
     """Same call signature and return values as the reference (functions.py:35-81,418).
 
     Keyword-only extensions: ``f0s`` ((n,3) [t,f0,strength] track, replaces SWIPE') and ``frames``
     ((speech5, voiced5, frame_step), replaces voicedUnvoicedFrames) let a caller supply the
     host preprocessing results (by default both are computed on the CPU by preprocess.py like the
-    reference does); ``loadingScreen`` is accepted and ignored (there is no per-frame Python loop).
+    reference does); ``loadingScreen`` is accepted and ignored (there is no per-frame Python loop);
+    ``return_tensors=True`` returns the per-frame parameters as the dense ``engine.Result`` (a0 (No_ti,), am / fm / ph
+    (No_ti, Kmax), flags) in place of the list of ``Deterministic`` objects, whose construction costs more than the
+    whole GPU path for one utterance (``pack_det_components(result)`` converts later; ``params.save_result`` /
+    ``params.resynthesize`` work on the tensor form).
     """
     from . import preprocess
     startTime = time()
@@ -121,7 +134,7 @@ def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', s
 
     res = analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender, step, maxAdpt, pitchPeriods,
                          analysisWindow, fullWaveform, partials, on_adaptation=prompt)
-    det = pack_det_components(res)
+    det = res if return_tensors else pack_det_components(res)
     endTime = time() - startTime
     if printPrompts:
         print('Signal adapted to {} dB SRER'.format(round(max(res.SRER), 6)))

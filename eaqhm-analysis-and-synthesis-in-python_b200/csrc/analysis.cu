@@ -10,6 +10,9 @@ namespace {
 constexpr int kBasisThreads = 256;
 constexpr int kBasisWarps = kBasisThreads / 32;
 constexpr int kNb = 16;   // Cholesky block width
+// A pivot below kPivotTol x the matrix's own diagonal entry means the normal matrix is singular to working precision
+// (legitimate frames: cond(R) <= ~2e7, pivots >= ~1e-8 of the diagonal); the frame is flagged and the host raises
+constexpr double kPivotTol = 1e-13;
 
 struct AnaArgs {
     eaqhm_tables t;
@@ -965,6 +968,7 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
     __shared__ double2 D[kNb][kNb + 1];               // factored diagonal block of the current block column
     __shared__ double2 Tall[kNW][kNb][kNb + 1];       // per-warp staging tile
     __shared__ double2 red[kThreads / 16][17];
+    __shared__ double Dorig[kNW][kNb];                // diagonal of R before the update: scale of the pivot test
     __shared__ int bad;
     extern __shared__ __align__(16) double2 xs[];     // [Pmax] solution
     double2 (*T)[kNb + 1] = Tall[warp];
@@ -1071,6 +1075,7 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
                             double2 v = make_double2(0.0, 0.0);
                             if (i <= P && cidx < nbc && jb + cidx <= i) {
                                 v = RF[(size_t)i * Pp + jb + cidx];
+                                if (rb == jbk && r == cidx) Dorig[warp][r] = v.x;
                                 v.x += wr[si][sj][e]; v.y += wi[si][sj][e];
                             }
                             T[r][cidx] = v;
@@ -1080,8 +1085,11 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
                 // ---- 2. diagonal tile: factor it in place (warp-synchronous), publish as D ----------
                 if (rb == jbk) {
                     for (int c = 0; c < nbc; c++) {
-                        const double dd = T[c][c].x;
-                        if (!(dd > 0.0) && lane == 0) bad = 1;
+                        double dd = T[c][c].x;
+                        if (!(dd > kPivotTol * Dorig[warp][c])) {   // not (numerically) positive definite: flag the frame (the host raises) and keep
+                            if (lane == 0) bad = 1;     // the factor finite so that nothing downstream sees NaN
+                            dd = 1.0;
+                        }
                         const double dsq = sqrt(dd), inv = 1.0 / dsq;
                         __syncwarp();
                         if (lane == c) T[c][c] = make_double2(dsq, 0.0);
@@ -1300,6 +1308,7 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_real(AnaArg
     __shared__ double D[kNb][kNb + 1];
     __shared__ double Tall[kNW][kNb][kNb + 1];
     __shared__ double red[kThreads / 16][17];
+    __shared__ double Dorig[kNW][kNb];
     __shared__ int bad;
     extern __shared__ __align__(16) double xsr[];     // [P] solution
     double (*T)[kNb + 1] = Tall[warp];
@@ -1349,14 +1358,21 @@ __global__ void __launch_bounds__(kNW * 32, 512 / (kNW * 32)) k_chol_real(AnaArg
                         for (int e = 0; e < 2; e++) {
                             const int r = si * 8 + lr, cidx = sj * 8 + 2 * lc + e, i = i0 + r;
                             double v = 0.0;
-                            if (i <= P && cidx < nbc && jb + cidx <= i) v = RF[(size_t)i * Pp + jb + cidx] + acc[si][sj][e];
+                            if (i <= P && cidx < nbc && jb + cidx <= i) {
+                                v = RF[(size_t)i * Pp + jb + cidx];
+                                if (rb == jbk && r == cidx) Dorig[warp][r] = v;
+                                v += acc[si][sj][e];
+                            }
                             T[r][cidx] = v;
                         }
                 __syncwarp();
                 if (rb == jbk) {
                     for (int c = 0; c < nbc; c++) {
-                        const double dd = T[c][c];
-                        if (!(dd > 0.0) && lane == 0) bad = 1;
+                        double dd = T[c][c];
+                        if (!(dd > kPivotTol * Dorig[warp][c])) {
+                            if (lane == 0) bad = 1;
+                            dd = 1.0;
+                        }
                         const double dsq = sqrt(dd), inv = 1.0 / dsq;
                         __syncwarp();
                         if (lane == c) T[c][c] = dsq;
@@ -1520,10 +1536,13 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
 }
 
 int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
-    static bool gram_attr = false;
-    if (!gram_attr) {
+    static DeviceOnce solve_once;               // function attributes are per device
+    if (const int dev = solve_once.claim(); dev != -1) {
+        CHECK_ARG(dev >= 0);
         CUDA_TRY(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
-        gram_attr = true;
+        CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     }
     // experiment knob (tools only): EAQHM_GRAM_VARIANT=1 selects the CTA-tiled kernel, 3 the warp kernel with four real
     // products per complex product; default: warp kernel with three (3M)
@@ -1533,16 +1552,7 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         dim3 grid(Tt * (Tt + 1) / 2, a.nf);
         LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
     } else if (do_gram) {
-        static bool g2_attr = false;
-        static int nsm = 148;
-        if (!g2_attr) {
-            CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
-            CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
-            int dev = 0;
-            CUDA_TRY(cudaGetDevice(&dev));
-            CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-            g2_attr = true;
-        }
+        const int nsm = eaqhm_sm_count();
         const int Tt16 = (a.Mxmax + 15) / 16, ipf = Tt16 * (Tt16 + 1) / 2;
         const long long nitems = (long long)a.nf * ipf;
         int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
@@ -1553,11 +1563,6 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     // experiment knob (tools only): EAQHM_CHOL_PAD_KB pads the dynamic shared memory to lower the frames per SM
     static const size_t pad = getenv("EAQHM_CHOL_PAD_KB") ? (size_t)atoi(getenv("EAQHM_CHOL_PAD_KB")) * 1024 : 0;
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2) + pad;
-    static bool chol_attr = false;
-    if (pad && !chol_attr) {
-        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        chol_attr = true;
-    }
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
     CHECK_ARG(xs_bytes - pad <= 32 * 1024);
@@ -1612,11 +1617,11 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     while (nwb > 1 && basis_smem_bytes(l.Lp, nwb) > 200 * 1024) nwb--;
     A.nwb = nwb;
     const size_t smem = basis_smem_bytes(l.Lp, nwb);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce basis_once;               // function attributes are per device
+    if (const int dev = basis_once.claim(); dev != -1) {
+        CHECK_ARG(dev >= 0);
         CUDA_TRY(cudaFuncSetAttribute(k_basis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(k_basis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     CHECK_ARG(smem <= 200 * 1024);
 

@@ -21,15 +21,16 @@ extern "C" int eaqhm_device_count(void) {
 }
 
 // ---- profiler: launch counts always, CUDA-event timing on request ---------------------------
+#include <mutex>
 #include <vector>
 namespace {
+std::mutex g_prof_mu;   // launches of different host threads share the accounting below
 struct Pending { int kc; cudaEvent_t e0, e1; };
 bool g_prof_on = false;
 long long g_counts[KC_COUNT] = {0};
 double g_ms[KC_COUNT] = {0};
 std::vector<Pending> g_pending;
 std::vector<cudaEvent_t> g_pool;
-cudaEvent_t g_cur = nullptr;
 cudaEvent_t take_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -45,25 +46,49 @@ void drain() {
 }
 }  // namespace
 
+// begin/end bracket one launch on one host thread: the start event travels in a thread-local slot, the shared
+// lists are touched under the mutex
+static thread_local cudaEvent_t t_cur = nullptr;
 void eaqhm_prof_begin(int kc, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_counts[kc]++;
-    if (!g_prof_on) return;
-    g_cur = take_event();
-    cudaEventRecord(g_cur, st);
+    if (!g_prof_on) { t_cur = nullptr; return; }
+    t_cur = take_event();
+    cudaEventRecord(t_cur, st);
 }
 void eaqhm_prof_end(int kc, cudaStream_t st) {
-    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_on || t_cur == nullptr) return;
     cudaEvent_t e1 = take_event();
     cudaEventRecord(e1, st);
-    g_pending.push_back({kc, g_cur, e1});
+    g_pending.push_back({kc, t_cur, e1});
+    t_cur = nullptr;
+}
+
+int eaqhm_sm_count() {
+    static int nsm[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    if (nsm[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        nsm[dev] = n;
+    }
+    return nsm[dev];
 }
 
 static const char* kKernelNames[KC_COUNT] = {"fallback_flags", "active", "basis", "gram", "chol_solve", "accept",
                                              "run_moments", "a0_moments", "interp", "synth", "reduce", "var_pass",
                                              "snapshot"};
 
-extern "C" int eaqhm_profile_enable(int on) { drain(); g_prof_on = on != 0; return EAQHM_OK; }
+extern "C" int eaqhm_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    drain();
+    g_prof_on = on != 0;
+    return EAQHM_OK;
+}
 extern "C" int eaqhm_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     drain();
     for (int i = 0; i < KC_COUNT; i++) { g_counts[i] = 0; g_ms[i] = 0.0; }
     return EAQHM_OK;
@@ -72,6 +97,7 @@ extern "C" int eaqhm_profile_classes(void) { return KC_COUNT; }
 extern "C" const char* eaqhm_profile_name(int kc) { return (kc >= 0 && kc < KC_COUNT) ? kKernelNames[kc] : ""; }
 extern "C" int eaqhm_profile_read(double* ms, int64_t* counts, int32_t n) {
     CHECK_ARG(ms && counts && n >= KC_COUNT);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     drain();
     for (int i = 0; i < KC_COUNT; i++) { ms[i] = g_ms[i]; counts[i] = g_counts[i]; }
     return EAQHM_OK;

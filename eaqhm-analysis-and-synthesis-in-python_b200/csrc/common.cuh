@@ -53,6 +53,23 @@ void eaqhm_prof_end(int kc, cudaStream_t st);
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+// ---- per-device one-time initialisation -------------------------------------------------------
+// cudaFuncSetAttribute and __constant__ uploads are per device: every such set-up is keyed by the CURRENT device's
+// ordinal (the caller makes the stream's device current: engine.py wraps every call in torch.cuda.device).
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+    bool done[kMaxDevices] = {};
+    // returns the current device ordinal when its set-up is still to do (and marks it done), -1 otherwise, -2 on error
+    int claim() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -2;
+        if (done[dev]) return -1;
+        done[dev] = true;
+        return dev;
+    }
+};
+int eaqhm_sm_count();   // multiprocessors of the current device (cached per device)
+
 // ---- complex helpers on double2 (x = re, y = im) ---------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);

@@ -411,14 +411,15 @@ __global__ void k_phase_integr_dense(const double* fm, const double* phc, const 
     }
 }
 
-bool g_cp_ready = false;
+DeviceOnce g_cp_once;
 int ensure_cp_table() {
-    if (g_cp_ready) return EAQHM_OK;
+    const int dev = g_cp_once.claim();          // __constant__ memory is per device
+    if (dev == -1) return EAQHM_OK;
+    CHECK_ARG(dev >= 0);
     double cp[kCpTab];
     cp[0] = 0.25;
     for (int i = 1; i < kCpTab; i++) cp[i] = 1.0 / (4.0 - cp[i - 1]);
     CUDA_TRY(cudaMemcpyToSymbol(c_cp, cp, sizeof(cp)));
-    g_cp_ready = true;
     return EAQHM_OK;
 }
 

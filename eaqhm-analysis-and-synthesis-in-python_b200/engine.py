@@ -53,6 +53,22 @@ class Result:
     ph: np.ndarray
     n_adapt_best: int = 0
     stats: dict = field(default_factory=dict)
+    fs: int = 0                     # sample rate and hop: what params.resynthesize / save_result need besides the arrays
+    step: int = 15
+
+
+class NotPositiveDefiniteError(np.linalg.LinAlgError):
+    """A frame's normal matrix E_w^H E_w was not positive definite.  The reference's explicit inverse
+    (functions.py:465,530) raises numpy.linalg.LinAlgError on an exactly singular matrix and returns noise on a
+    numerically singular one; the Cholesky solve of this path detects both and refuses to return that noise."""
+
+
+def check_not_pd(count):
+    if count:
+        raise NotPositiveDefiniteError(
+            "%d frame solve(s) met a normal matrix that is not positive definite (window shorter than the number of "
+            "unknowns, e.g. pitchPeriods <= 2, or an all-zero window); the reference's inv() raises LinAlgError or "
+            "returns noise for such frames (functions.py:465,530)" % int(count))
 
 
 _h2d_counter = [0]
@@ -298,6 +314,10 @@ class Engine:
         """Stage A (functions.py:176-329)."""
         for x in self.kn:
             x.zero_()
+        with torch.cuda.device(self.device):          # the library launches on the current device
+            self._analysis(a)
+
+    def _analysis(self, a):
         _lib.check(self.L.eaqhm_analysis(C.byref(self.tab), self.s.data_ptr(), C.byref(self.c_tr), C.byref(self.c_kn),
                                          self.best_am_ptr or self.best[0].data_ptr(), a, self.nnz_max, self.N_max,
                                          self.chunk,
@@ -306,12 +326,21 @@ class Engine:
 
     def interpolate(self):
         """Stage B (functions.py:337-383)."""
+        with torch.cuda.device(self.device):
+            self._interpolate()
+
+    def _interpolate(self):
         _lib.check(self.L.eaqhm_interpolate(C.byref(self.tab), C.byref(self.c_kn), C.byref(self.c_tr),
                                             self.fm_fin.data_ptr(), self.a0mom.data_ptr(), self.iwork.data_ptr(),
                                             self.iwork.numel(), self._stream()))
 
     def synthesize(self):
         """Stage C (functions.py:385-388); returns [mean | M2] of the residual per utterance (device tensor)."""
+        with torch.cuda.device(self.device):
+            self._synthesize()
+        return self.stat
+
+    def _synthesize(self):
         _lib.check(self.L.eaqhm_synthesize(C.byref(self.tab), C.byref(self.c_tr), self.kn[3].data_ptr(),
                                            self.a0mom.data_ptr(), self.det.data_ptr(), self.s_hat.data_ptr(),
                                            self.stat.data_ptr(), self.swork.data_ptr(), self.swork.numel(),
@@ -325,6 +354,10 @@ class Engine:
 
     def snapshot(self, improved):
         self.improved.copy_(torch.from_numpy(np.asarray(improved, bool).astype(np.uint8)))
+        with torch.cuda.device(self.device):
+            self._snapshot()
+
+    def _snapshot(self):
         _lib.check(self.L.eaqhm_snapshot(C.byref(self.tab), self.improved.data_ptr(), C.byref(self.c_tr),
                                          C.byref(self.c_kn), self.fm_fin.data_ptr(), self.a0mom.data_ptr(),
                                          self.s_hat.data_ptr(), self.s_best.data_ptr(), C.byref(self.c_best),
@@ -367,6 +400,7 @@ class Engine:
                 break
         fl = self.flops.cpu().numpy()
         self.useful_flops = dict(gram=float(fl[0]), chol=float(fl[1]), basis=float(fl[2]))
+        check_not_pd(int(self.status[0].item()))
         return SRER, best_a, frames_solved
 
     def run(self, on_adaptation=None):
@@ -390,7 +424,7 @@ class Engine:
                 s_recon=s_best[self.ustart[i]:self.ustart[i] + f.length].copy(), SRER=list(SRER[i]), ti=f.ti0.copy(),
                 isSpeech=f.isSpeech.copy(), isVoiced=f.analysed.copy(), a0=b_a0[sl].copy(),
                 am=b_am[sl, :ku].copy(), fm=b_fm[sl, :ku].copy(), ph=b_ph[sl, :ku].copy(),
-                n_adapt_best=int(best_a[i]),
+                n_adapt_best=int(best_a[i]), fs=int(self.fs), step=self.step,
                 stats=dict(not_pd_frames=int(status[0]), fallback_frames=int(status[1]),
                            frames_solved=int(frames_solved))))
         return out

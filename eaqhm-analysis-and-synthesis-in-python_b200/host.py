@@ -105,6 +105,13 @@ class FrameTables:
         self.own = np.full(self.No_ti, step, np.int32)
         self.own[-1] = length - self.ti0[-1]
 
+    def wrapping_frames(self):
+        """Analysed frames whose window starts before sample 0: the reference's fancy index wraps those samples to
+        the END of the signal (functions.py:196,244-245; happens when N > analysisWindow*step, e.g. 44.1/48 kHz
+        with f0 below ~150 Hz at the default analysisWindow).  The monolithic engine reproduces that; a frame-range
+        excerpt cannot (the tail belongs to another shard), so the streamed engine refuses such signals."""
+        return np.flatnonzero(self.analysed & (self.ti0 < self.N))
+
     def excerpt(self, lo, hi):
         """Tables of the sample range [lo, hi) of this signal (lo a multiple of step), with the SAME per-frame
         values as the whole signal's (f0, K, N, flags are sliced, not recomputed, so a frame-range shard analyses

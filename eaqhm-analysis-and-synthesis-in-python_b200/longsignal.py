@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import BufferPool, Engine, Result, Utterance, _to_host, merge_stats
+from .engine import BufferPool, Engine, Result, Utterance, _to_host, check_not_pd, merge_stats
 from .host import FrameTables
 from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks
 
@@ -123,6 +123,11 @@ class LongSignalEngine:
         self.full = full_tables if full_tables is not None else FrameTables(
             len(s), fs, f0s, voiced5, frame_step, Kmax, step, pitchPeriods, analysisWindow)
         full = self.full
+        if len(full.wrapping_frames()):
+            raise ValueError("%d analysed frame(s) have a window that starts before sample 0 (the reference wraps it to "
+                             "the end of the signal): not supported by the frame-range engine; use engine.Engine, or "
+                             "raise analysisWindow so that analysisWindow*step >= the largest half window (%d samples)"
+                             % (len(full.wrapping_frames()), int(full.N.max())))
         align = int(np.lcm(self.step, int(frame_step)))
         self.halo = exchange_halo_samples(int(full.N.max()), self.step, analysisWindow, align)
         self.H = self.halo // self.step
@@ -260,6 +265,7 @@ class LongSignalEngine:
             best_a = a
         fl = self.pool.get("flops", 3, torch.float64).cpu().numpy()
         self.useful_flops = dict(gram=float(fl[0]), chol=float(fl[1]), basis=float(fl[2]))
+        check_not_pd(int(self.pool.get("status", 2, torch.int32)[0].item()))
         return SRER, best_a, solves
 
     def results(self, SRER, best_a, solves=0):
@@ -286,6 +292,7 @@ class LongSignalEngine:
         self.d2h_bytes += (self.R_hi - self.R_lo) * 8 + n * (3 * K + 1) * 8
         return Result(s_recon=s_recon, SRER=list(SRER), ti=full.ti0.copy(), isSpeech=full.isSpeech.copy(),
                       isVoiced=full.analysed.copy(), a0=a0, am=am, fm=fm, ph=ph, n_adapt_best=int(best_a),
+                      fs=int(self.fs), step=self.step,
                       stats=dict(shards=len(self.shards), frames_solved=int(solves), not_pd_frames=int(status[0]),
                                  fallback_flags=int(status[1]), exchanged_bytes=int(self.exchanged_bytes),
                                  owned_samples=(self.R_lo, self.R_hi), owned_frames=(self.F_lo, self.F_hi)))

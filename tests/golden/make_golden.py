@@ -143,6 +143,21 @@ def case_synth_48k():
     make_case("synth_48k", pcm, 48000, (70, 100), f0s, maxAdpt=1, analysisWindow=64)
 
 
+def case_c2_2s():
+    """First 2 s of the c2 signal (f0 sweeping 90-250 Hz): the streamed long-signal engine is compared with this
+    reference run in two or more frame-range shards (tests/test_gpu_parity.py)."""
+    cfg = synthetic.config_c2(duration=2.0)
+    pcm, f0s = synth_pcm(cfg)
+    make_case("c2_2s", pcm, 16000, (90, 250), f0s, subsample=3, maxAdpt=2)
+
+
+def case_c4_015():
+    """0.15 s of the c4 configuration (48 kHz, f0 ~ 80 Hz, P = 1,190), two adaptive passes."""
+    cfg = synthetic.config_c4(duration=0.15)
+    pcm, f0s = synth_pcm(cfg)
+    make_case("c4_015", pcm, 48000, (70, 100), f0s, subsample=2, maxAdpt=2, analysisWindow=64)
+
+
 def silence_pcm():
     """Harmonic signal with two stretches of digital silence: frames whose window is all zeros accept nothing at
     adaptation 0 and take the 140 Hz fallback afterwards (functions.py:204-242, quirks Q6/Q10)."""
@@ -209,7 +224,7 @@ CASES = {
     "synth_a0": lambda: case_synth_a(0), "synth_a1": lambda: case_synth_a(1),
     "synth_a2": lambda: case_synth_a(2), "synth_a3": lambda: case_synth_a(3),
     "synth_low": case_synth_low, "synth_child_vo": case_synth_child_voiced_only,
-    "synth_48k": case_synth_48k, "synth_silence": case_synth_silence, "sa19": case_sa19,
+    "synth_48k": case_synth_48k, "c2_2s": case_c2_2s, "c4_015": case_c4_015, "synth_silence": case_synth_silence, "sa19": case_sa19,
 }
 
 if __name__ == "__main__":

@@ -1,10 +1,18 @@
 """GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the golden fixtures made by
 the reference and against the oracle on seeded inputs.
 
-Tolerances (north_star): waveform 1e-7 absolute, SRER 0.01 dB, amplitudes / frequencies 1e-9 relative.
-"Relative" is taken per frame against the frame's largest amplitude for amplitudes, and per harmonic for
-the frequencies of harmonics within 60 dB of the frame maximum: weaker harmonics are below the
-conditioning noise of the reference's own normal-equation solve (cond(R) up to 1e6).
+Tolerances (north_star): waveform 1e-7 absolute, SRER 0.01 dB, amplitudes / frequencies 1e-9 relative, all of
+them asserted here through tests/common.tolerance():
+  am_rel_framemax   amplitudes against the frame's largest amplitude                      1e-9
+  am_rel_strong     amplitudes per harmonic (harmonics within 60 dB of the frame maximum) max(1e-9, 10 x floor)
+  fm_rel_strong     frequencies per harmonic (same harmonics)                             max(1e-9, 10 x floor)
+  ph_abs_strong     phases (rad, same harmonics)                                          max(1e-9, 10 x floor)
+  a0_abs            DC component                                                          1e-9
+`floor` is the reference's own run-to-run noise on the same fixture (the unmodified reference re-run with one
+instead of eight OpenBLAS threads; tests/golden/make_floor.py -> tests/golden/floors.json): two runs of the
+reference differ per harmonic by 0.5-1.7e-10 after one to four adaptations on the 0.4 s fixtures already, because
+its explicit inverse (functions.py:465,530) is noisy at cond(R) up to 1e6 and the adaptation loop feeds that back.
+Harmonics more than 60 dB below the frame maximum sit below that noise and are checked through am_rel_framemax only.
 """
 import ctypes as C
 
@@ -12,7 +20,7 @@ import numpy as np
 import pytest
 
 import eaqhm_oracle as O
-from common import GOLDEN, compare_to_golden, inputs_from_golden, load_golden
+from common import GOLDEN, KEYS, compare_to_golden, inputs_from_golden, load_golden, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -58,6 +66,10 @@ def assert_close_results(res, ref):
     assert ((res.fm[v] == 0) == (ref.fm[v] == 0)).all()
     assert (np.abs(res.fm[v] - ref.fm[v])[strong] / np.abs(ref.fm[v][strong])).max() <= TOL_REL
     assert np.abs(res.a0 - ref.a0).max() <= TOL_REL
+    # per-harmonic relative amplitude and absolute phase of the harmonics within 60 dB of the frame maximum
+    sa = ref.am[v] > 1e-3 * fmax
+    assert (np.abs(res.am[v] - ref.am[v])[sa] / ref.am[v][sa]).max() <= tolerance(None, "am_rel_strong")
+    assert np.abs(res.ph[v] - ref.ph[v])[sa].max() <= tolerance(None, "ph_abs_strong")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -169,19 +181,41 @@ def test_phase_seam_random_segments(lib):
 # whole path against the reference's golden outputs
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["synth_a_adpt0", "synth_a_adpt1", "synth_a_adpt2", "synth_a_adpt3", "synth_low",
-                                  "synth_child_vo", "synth_48k", "synth_silence", "sa19"])
+                                  "synth_child_vo", "synth_48k", "synth_silence", "c2_2s", "c4_015", "sa19"])
 def test_cuda_path_matches_reference_golden(name):
     g, kw = load_golden(name)
     res = run_cuda(inputs_from_golden(g, kw))
     c = compare_to_golden(res, g)
     assert c["n_adapt"][0] == c["n_adapt"][1], c
-    assert c["flags_ok"] and c["support_equal"], c
-    assert c["dSRER"] <= TOL_SRER, c
-    assert c["ds"] <= TOL_S, c
-    assert c["am_rel_framemax"] <= TOL_REL, c
-    assert c["fm_rel_strong"] <= TOL_REL, c
-    assert c["a0_abs"] <= TOL_REL, c
+    assert c["flags_ok"] and c["support_equal"] and c["fm_zero_equal"], c
+    for key in KEYS:                                   # SRER, samples, amplitudes (two ways), frequencies, phases, DC
+        assert c[key] <= tolerance(name, key), (key, c)
     assert res.stats["not_pd_frames"] == 0
+
+
+def test_streamed_c2_shards_match_the_reference():
+    """an excerpt of the c2 signal across shard boundaries against the REFERENCE (not against the
+    monolithic CUDA run): 2 s streamed as four and as two frame-range shards."""
+    g, kw = load_golden("c2_2s")
+    inp = inputs_from_golden(g, kw)
+    for shard_seconds, nsh in ((0.5, 4), (1.0, 2)):
+        res, eng = run_streamed(inp, shard_seconds)
+        assert len(eng.shards) == nsh
+        c = compare_to_golden(res, g)
+        assert c["n_adapt"][0] == c["n_adapt"][1] and c["flags_ok"] and c["support_equal"] and c["fm_zero_equal"], c
+        for key in KEYS:
+            assert c[key] <= tolerance("c2_2s", key), (shard_seconds, key, c)
+
+
+def test_not_positive_definite_frames_raise():
+    """A window shorter than the unknown count (pitchPeriods=1 at f0 ~ 100 Hz: L = 241 samples, P = 2(2K+1) = 314) makes
+    E_w^H E_w singular.  The reference's inv() raises LinAlgError or returns noise (functions.py:465,530); this path raises
+    a LinAlgError subclass instead of handing NaN or noise on."""
+    from eaqhm_b200 import engine
+    g, kw = load_golden("synth_low")
+    inp = inputs_from_golden(g, kw)
+    with pytest.raises(np.linalg.LinAlgError):
+        engine.Engine([utterance(inp)], maxAdpt=1, pitchPeriods=1).run()
 
 
 def test_sa19_srer_matches_published_values():
@@ -493,3 +527,43 @@ def test_non_default_parameters_match_oracle(kw):
     ref = O.eaqhm_oracle(s, 16000, f0s, np.ones(n5, bool), 80, 90.0, Kmax, step=step, maxAdpt=2, pitchPeriods=pp,
                          analysisWindow=aw)
     assert_close_results(res, ref)
+
+
+def test_resynthesis_from_parameters_and_compact_format(tmp_path):
+    """the dense parameter tensors -> compact file -> back -> waveform through eaqhm_interpolate +
+    eaqhm_synthesize.  The returned phases are the reference's pm_fin (functions.py:402): at the last frame of a run that is
+    the INTEGRATED phase, not the measured one, so the last hop of every run is rebuilt from slightly different knots (the
+    sinusoidal correction of functions.py:565-569 is re-derived against its own end value: 0.4 % of that correction);
+    everywhere else the waveform is the analysis' own s_recon to rounding."""
+    from eaqhm_b200 import params
+    g, kw = load_golden("synth_a_adpt3")
+    inp = inputs_from_golden(g, kw)
+    res = run_cuda(inp)
+    path = str(tmp_path / "p.npz")
+    params.save_result(path, res)
+    back = params.load_result(path)
+    for a, b in ((res.am, back.am), (res.fm, back.fm), (res.ph, back.ph), (res.a0 * res.isVoiced, back.a0)):
+        assert (a == b).all()
+    assert (back.isVoiced == res.isVoiced).all() and (back.isSpeech == res.isSpeech).all() and (back.ti == res.ti).all()
+    assert back.SRER == [float(x) for x in res.SRER] and back.fs == 16000 and back.step == 15
+    s = params.resynthesize(back)
+    v = np.flatnonzero(res.isVoiced)
+    lo, hi = res.ti[v[0]], res.ti[v[-1]] - 15            # all runs of this fixture end at the last analysed frame
+    assert np.abs(s[lo:hi] - res.s_recon[lo:hi]).max() <= 1e-12
+    assert np.abs(s - res.s_recon).max() <= 2e-3 * np.abs(res.s_recon).max()
+    srer = 20 * np.log10(np.std(res.s_recon) / np.std(s - res.s_recon))
+    assert srer > 60.0
+
+
+def test_api_returns_tensors_on_request(tmp_path):
+    from scipy.io import wavfile
+    from eaqhm_b200 import engine
+    from eaqhm_b200.api import eaQHMAnalysisAndSynthesis
+    g, kw = load_golden("synth_a_adpt1")
+    wav = str(tmp_path / "a.wav")
+    wavfile.write(wav, int(g["fs"]), g["pcm"])
+    s_recon, SRER, res, t = eaQHMAnalysisAndSynthesis(wav, (90, 250), maxAdpt=1, printPrompts=False, f0s=g["f0s"],
+                                                      frames=(g["speech5"], g["voiced5"], int(g["frame_step"])),
+                                                      return_tensors=True)
+    assert isinstance(res, engine.Result) and res.am.shape == (len(res.ti), int(g["Kmax"]))
+    assert np.abs(s_recon - g["s_recon"]).max() <= TOL_S and np.abs(np.array(SRER) - g["SRER"]).max() <= TOL_SRER

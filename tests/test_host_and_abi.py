@@ -146,3 +146,54 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("c2")
+
+
+def test_wrapping_windows_are_reported_and_refused_by_the_streamed_engine():
+    """A window that starts before sample 0 wraps to the END of the signal in the reference (functions.py:196 with a
+    negative start index): 48 kHz, f0 = 80 Hz, default analysisWindow -> N = 900 > 480.  The monolithic engine
+    reproduces it; a frame-range excerpt cannot, so FrameTables reports such frames for the streamed engine's guard."""
+    import numpy as np
+    from eaqhm_b200 import host
+    fs, length = 48000, 48000
+    n5 = len(np.arange(1, length, 240))
+    t = np.arange(0, length - 1, 240) / fs
+    f0s = np.stack([t, np.full(len(t), 80.0), np.ones(len(t))], axis=1)
+    v5 = np.ones(n5, bool)
+    v5[-6:] = False                  # the reference raises IndexError on a window past the END (FrameTables too)
+    ft = host.FrameTables(length, fs, f0s, v5, 240, 300)
+    w = ft.wrapping_frames()
+    assert len(w) > 0 and (ft.ti0[w] < ft.N[w]).all() and ft.ti0[w].min() >= 480
+    ft64 = host.FrameTables(length, fs, f0s, v5, 240, 300, analysisWindow=64)
+    assert len(ft64.wrapping_frames()) == 0
+
+
+def test_not_positive_definite_error_is_a_linalg_error():
+    import numpy as np
+    from eaqhm_b200 import engine
+    assert issubclass(engine.NotPositiveDefiniteError, np.linalg.LinAlgError)
+    engine.check_not_pd(0)
+    import pytest
+    with pytest.raises(np.linalg.LinAlgError):
+        engine.check_not_pd(3)
+
+
+def test_compact_parameter_file_round_trip(tmp_path):
+    """params.save_result / load_result on a hand-made result: no GPU involved."""
+    import numpy as np
+    from eaqhm_b200 import engine, params
+    rng = np.random.default_rng(0)
+    length, step, K = 1000, 15, 7
+    n = len(np.arange(1, length, step))
+    voiced = rng.random(n) < 0.7
+    am = rng.random((n, K)) * (rng.random((n, K)) < 0.6) * voiced[:, None]
+    fm = (am != 0) * rng.uniform(100, 7000, (n, K))
+    ph = (am != 0) * rng.uniform(-3, 3, (n, K))
+    res = engine.Result(s_recon=rng.standard_normal(length), SRER=[10.0, 12.5], ti=np.arange(0, length - 1, step),
+                        isSpeech=voiced | (rng.random(n) < 0.1), isVoiced=voiced, a0=rng.standard_normal(n) * voiced,
+                        am=am, fm=fm, ph=ph, n_adapt_best=1, fs=16000, step=step)
+    p = str(tmp_path / "r.npz")
+    params.save_result(p, res, include_waveform=True)
+    back = params.load_result(p)
+    for name in ("s_recon", "ti", "isSpeech", "isVoiced", "a0", "am", "fm", "ph"):
+        assert (getattr(back, name) == getattr(res, name)).all(), name
+    assert back.SRER == res.SRER and back.n_adapt_best == 1 and back.fs == 16000 and back.step == step
