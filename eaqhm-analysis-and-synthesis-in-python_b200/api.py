@@ -61,16 +61,38 @@ STREAM_THRESHOLD_BYTES = 8 << 30     # dense tracks (5 x Kmax x length doubles) 
 MONOLITHIC_LIMIT_BYTES = 100 << 30   # ... unless the signal has wrapping windows and still fits one GPU
 
 
-def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10,
-                   pitchPeriods=3, analysisWindow=32, fullWaveform=True, partials=0, on_adaptation=None,
-                   stream_threshold_bytes=None, shard_seconds=20.0):
-    """The hot path on array-level inputs (SURVEY.md §8b); returns an engine.Result.  Signals whose dense
-    per-sample tracks would not fit comfortably (the reference's layout needs length x Kmax x 7 doubles,
-    functions.py:159-171) go through the streamed long-signal engine, which gives the same result."""
+class PathHandle:
+    """The resident form of one analyze_arrays call: inputs on the device, engine built.  ``run_device`` repeats the
+    adaptation loop on the resident inputs (what bench.py times as `value`), ``results`` copies one run's outputs to
+    host arrays; ``analyze_arrays`` is make_engine(...).run()."""
+
+    def __init__(self, eng, single):
+        self.eng, self.single = eng, single
+
+    def run_device(self, on_adaptation=None, fixed_adaptations=None, prefetch_results=False):
+        cb = on_adaptation
+        if cb is not None and not self.single:
+            cb = lambda a, SRER: on_adaptation(a, [SRER])           # the long-signal engine keeps one SRER list
+        return self.eng.run_device(cb, fixed_adaptations=fixed_adaptations, prefetch_results=prefetch_results)
+
+    def results(self, out):
+        r = self.eng.results(*out)
+        return r[0] if self.single else r
+
+    def run(self, on_adaptation=None, fixed_adaptations=None):
+        return self.results(self.run_device(on_adaptation, fixed_adaptations, prefetch_results=True))
+
+
+def make_engine(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10, pitchPeriods=3,
+                analysisWindow=32, fullWaveform=True, partials=0, stream_threshold_bytes=None, shard_seconds=20.0,
+                rank=0, world=1, dist=None, **engine_kw):
+    """Host arrays -> PathHandle.  One GPU and dense tracks that fit: the monolithic engine.  Otherwise (tracks above
+    the streaming threshold, or world > 1: this rank analyses its contiguous frame range of the signal and exchanges
+    halos with its neighbours through `dist`) the frame-range engine."""
     u = make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender, step, analysisWindow, fullWaveform, partials)
     limit = STREAM_THRESHOLD_BYTES if stream_threshold_bytes is None else stream_threshold_bytes
-    stream = 5 * 8 * u.Kmax * len(u.s) > limit
-    if stream:
+    stream = world > 1 or 5 * 8 * u.Kmax * len(u.s) > limit
+    if stream and world == 1:
         # a window that wraps to the end of the signal (functions.py:196 with a negative start index) is only
         # reproduced by the monolithic engine: keep such signals there as long as their tracks fit at all
         ft = host.FrameTables(len(u.s), u.fs, u.f0s, u.voiced5, u.frame_step, u.Kmax, step, pitchPeriods, analysisWindow)
@@ -80,11 +102,24 @@ def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", ste
         from .longsignal import LongSignalEngine
         eng = LongSignalEngine(u.s, u.fs, u.f0s, u.voiced5, u.frame_step, u.f0min, u.Kmax, shard_seconds=shard_seconds,
                                det_part=u.det_part, step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods,
-                               analysisWindow=analysisWindow)
-        cb = None if on_adaptation is None else (lambda a, SRER: on_adaptation(a, [SRER]))
-        return eng.run(cb)
-    eng = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow)
-    return eng.run(on_adaptation)[0]
+                               analysisWindow=analysisWindow, rank=rank, world=world, dist=dist, **engine_kw)
+        return PathHandle(eng, single=False)
+    eng = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow, **engine_kw)
+    return PathHandle(eng, single=True)
+
+
+def analyze_arrays(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=15, maxAdpt=10,
+                   pitchPeriods=3, analysisWindow=32, fullWaveform=True, partials=0, on_adaptation=None,
+                   stream_threshold_bytes=None, shard_seconds=20.0, rank=0, world=1, dist=None,
+                   fixed_adaptations=None, **engine_kw):
+    """The hot path on array-level inputs (SURVEY.md §8b); returns an engine.Result.  Signals whose dense
+    per-sample tracks would not fit comfortably (the reference's layout needs length x Kmax x 7 doubles,
+    functions.py:159-171) go through the streamed long-signal engine, which gives the same result.  With
+    world > 1 (one process per GPU, `dist` = torch.distributed) the call is collective: every rank passes the whole
+    signal and gets its own contiguous range of the result inside full-length arrays."""
+    h = make_engine(s, fs, f0s, speech5, voiced5, frame_step, gender, step, maxAdpt, pitchPeriods, analysisWindow,
+                    fullWaveform, partials, stream_threshold_bytes, shard_seconds, rank, world, dist, **engine_kw)
+    return h.run(on_adaptation, fixed_adaptations)
 
 
 def analyze_batch(utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32, **engine_kw):

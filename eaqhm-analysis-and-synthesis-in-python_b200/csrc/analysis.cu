@@ -943,6 +943,163 @@ __global__ void __launch_bounds__(256) k_gram_toeplitz(AnaArgs A) {
 //      row, and writes the final rows; a second barrier closes the block column.
 // Row P of the augmented matrix carries conj(b); after the factorisation it holds y^H with L y = b.
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// Two-level (panel) left-looking Cholesky.  The factorisation advances in column panels of kPanelW = 48 columns.
+// For panel J, k_chol_update first applies ALL earlier panels to the panel's tiles,
+//     W[i, J] = R[i, J] - L[i, 0:Jb] L[Jb:Jb+48, 0:Jb]^H        (i >= Jb, in place),
+// as one dependency-free batched GEMM, then k_chol_solve(panel = J) factors the panel (its own update loop only spans
+// the <= 32 columns inside the panel).  80 % of the factorisation's flops move into the update kernel, which is built
+// like k_gram_warp: every warp owns one 16-row x 48-column tile end to end, streams its 16 A rows and the panel's 48 B
+// rows of the factor through a private double-buffered cp.async ring (8 factor columns per stage) and never meets a
+// barrier; 36 DMMAs (3M: three real products per complex product) per eight 16-byte fragment loads, where the
+// single-kernel version issued 16 DMMAs per four 16-byte loads straight from L2 / HBM.  Work items (frame, row tile) are
+// dealt round-robin to a persistent grid.
+// ---------------------------------------------------------------------------------------
+constexpr int kPanelW = 48;                           // columns per panel (three 16-wide block columns)
+constexpr int kUK = 8;                                // factor columns per pipeline stage
+constexpr int kUPitch = 12;                           // row pitch of a stage in double2: 8 + 4 pad = 192 B == 64 mod 128
+constexpr int kUStage = (16 + kPanelW) * kUPitch;     // double2 per stage: 16 A rows, then 48 B rows
+constexpr int kUWarps = 4;
+constexpr int kUpdSmem = kUWarps * 2 * kUStage * 16;
+
+template <bool k3M>
+__global__ void __launch_bounds__(kUWarps * 32, 2) k_chol_update(SolveArgs A, int panel, int items_per_frame) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    double2* ring = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * 2 * kUStage;
+    const long long nitems = (long long)A.nf * items_per_frame;
+    const long long gw = (long long)blockIdx.x * kUWarps + warp, nw = (long long)gridDim.x * kUWarps;
+    const int Jb = panel * kPanelW, rt0 = Jb / kNb;
+    const int Pp = A.Pp;
+
+    for (long long item = gw; item < nitems; item += nw) {
+        const int jl = (int)(item / items_per_frame), rt = rt0 + (int)(item - (long long)jl * items_per_frame);
+        const int P = 2 * A.Mcols[jl] + 2 * A.dc;
+        const int i0 = rt * kNb;
+        if (i0 > P || Jb >= P) continue;              // past the rhs row / frame already factored
+        double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * Pp;
+
+        // 8x8 sub-tiles that hold an element on or below the diagonal, inside the matrix
+        bool act_[2][3][2];
+#pragma unroll
+        for (int si = 0; si < 2; si++)
+#pragma unroll
+            for (int cb = 0; cb < 3; cb++)
+#pragma unroll
+                for (int sj = 0; sj < 2; sj++) {
+                    const int r0 = i0 + si * 8, c0 = Jb + cb * 16 + sj * 8;
+                    act_[si][cb][sj] = (r0 <= P) && (c0 < P) && (c0 <= r0 + 7);
+                }
+        // plain: acc[..][0] = Re, [1] = Im of sum a conj(b) (4 real products).  3M: [0] = sum ar br, [1] = sum ai bi,
+        // [2] = sum (ar + ai)(br - bi); Re = [0] + [1], Im = [2] - [0] + [1].
+        constexpr int kAcc = k3M ? 3 : 2;
+        double acc[2][3][2][kAcc][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+#pragma unroll
+                    for (int d = 0; d < kAcc; d++) acc[a][b][c][d][0] = acc[a][b][c][d][1] = 0.0;
+
+        // stage loader: 16 A rows (this tile's rows) and 48 B rows (the panel's rows) x 8 factor columns, 16 B pieces;
+        // rows past the matrix are clamped to the rhs row (their products are never stored)
+        auto load_stage = [&](int chunk, int slot) {
+            double2* dst = ring + (size_t)slot * kUStage;
+            const int k0 = chunk * kUK;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int idx = lane + e * 32, row = idx >> 3, kc = idx & 7;
+                cp_async16(dst + row * kUPitch + kc, RF + (size_t)min(i0 + row, P) * Pp + k0 + kc, 16);
+            }
+#pragma unroll
+            for (int e = 0; e < 12; e++) {
+                const int idx = lane + e * 32, row = idx >> 3, kc = idx & 7;
+                cp_async16(dst + (16 + row) * kUPitch + kc, RF + (size_t)min(Jb + row, P) * Pp + k0 + kc, 16);
+            }
+        };
+
+        const int nst = Jb / kUK;
+        load_stage(0, 0);
+        cp_async_commit();
+        for (int c = 0; c < nst; c++) {
+            if (c + 1 < nst) {
+                load_stage(c + 1, (c + 1) & 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const double2* st = ring + (size_t)(c & 1) * kUStage;
+            const double2* a_s = st + lr * kUPitch + lc;
+            const double2* b_s = st + (16 + lr) * kUPitch + lc;
+#pragma unroll
+            for (int kk = 0; kk < kUK; kk += 4) {
+                double ar[2], ai[2], ax[2];
+#pragma unroll
+                for (int si = 0; si < 2; si++) {
+                    const double2 v = a_s[si * 8 * kUPitch + kk];
+                    ar[si] = v.x; ai[si] = v.y;
+                    ax[si] = k3M ? v.x + v.y : -v.x;
+                }
+#pragma unroll
+                for (int cb = 0; cb < 3; cb++) {
+                    double br[2], bi[2], bx[2];
+#pragma unroll
+                    for (int sj = 0; sj < 2; sj++) {
+                        const double2 v = b_s[(cb * 16 + sj * 8) * kUPitch + kk];
+                        br[sj] = v.x; bi[sj] = v.y;
+                        bx[sj] = v.x - v.y;
+                    }
+#pragma unroll
+                    for (int si = 0; si < 2; si++)
+#pragma unroll
+                        for (int sj = 0; sj < 2; sj++)
+                            if (act_[si][cb][sj]) {
+                                if (k3M) {
+                                    dmma884(acc[si][cb][sj][0], ar[si], br[sj]);
+                                    dmma884(acc[si][cb][sj][1], ai[si], bi[sj]);
+                                    dmma884(acc[si][cb][sj][kAcc - 1], ax[si], bx[sj]);
+                                } else {
+                                    // a conj(b): Re += ar br + ai bi ; Im += ai br - ar bi
+                                    dmma884(acc[si][cb][sj][0], ar[si], br[sj]);
+                                    dmma884(acc[si][cb][sj][0], ai[si], bi[sj]);
+                                    dmma884(acc[si][cb][sj][1], ai[si], br[sj]);
+                                    dmma884(acc[si][cb][sj][1], ax[si], bi[sj]);
+                                }
+                            }
+                }
+            }
+            __syncwarp();
+        }
+
+        // epilogue: W = R - acc in place; C fragment element (row lr, cols 2 lc, 2 lc + 1) of each 8x8 sub-tile
+#pragma unroll
+        for (int si = 0; si < 2; si++)
+#pragma unroll
+            for (int cb = 0; cb < 3; cb++)
+#pragma unroll
+                for (int sj = 0; sj < 2; sj++) {
+                    if (!act_[si][cb][sj]) continue;
+                    const int i = i0 + si * 8 + lr;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int cidx = Jb + cb * 16 + sj * 8 + 2 * lc + e;
+                        if (i > P || cidx >= P || cidx > i) continue;
+                        const double p0 = acc[si][cb][sj][0][e], p1 = acc[si][cb][sj][1][e];
+                        const double re = k3M ? p0 + p1 : p0;
+                        const double im = k3M ? (acc[si][cb][sj][kAcc - 1][e] - p0) + p1 : p1;
+                        double2 v = RF[(size_t)i * Pp + cidx];
+                        v.x -= re; v.y -= im;
+                        RF[(size_t)i * Pp + cidx] = v;
+                    }
+                }
+    }
+}
+
 #ifdef EAQHM_CHOL_TIMING
 __device__ unsigned long long g_chol_cycles[8];
 #define TMARK(slot) do { if (lane == 0) { const long long _t = clock64(); tacc[slot] += _t - tlast; tlast = _t; } } while (0)
@@ -954,11 +1111,15 @@ __device__ unsigned long long g_chol_cycles[8];
 #define EAQHM_CHOL_3M 0
 #endif
 constexpr bool kChol3M = EAQHM_CHOL_3M != 0;
+
 template <int kNW>
 #ifndef EAQHM_CHOL_THREADS_PER_SM
 #define EAQHM_CHOL_THREADS_PER_SM 512
 #endif
-__global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 32)) k_chol_solve(SolveArgs A) {
+__global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 32)) k_chol_solve(SolveArgs A, int panel) {
+    // panel < 0: the whole factorisation and the back substitution in one launch.  panel = J >= 0: only the block columns
+    // of column panel J (kPanelW columns), whose tiles k_chol_update has already updated with every earlier panel, so the
+    // update loop below starts at the panel's first column; the back substitution runs in the frame's last panel.
     constexpr int kThreads = kNW * 32;
     const int jl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane >> 2, lc = lane & 3;
@@ -981,7 +1142,11 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
 
     const int nrb = (P + 1 + kNb - 1) / kNb;          // row blocks (the rhs row P is in the last one)
     const int ncb = (P + kNb - 1) / kNb;              // block columns
-    for (int jbk = 0; jbk < ncb; jbk++) {
+    const int jbk_lo = panel < 0 ? 0 : panel * (kPanelW / kNb);
+    const int jbk_hi = panel < 0 ? ncb : min(ncb, jbk_lo + kPanelW / kNb);
+    if (jbk_lo >= ncb) return;                        // this frame's factorisation ended in an earlier panel
+    const int kbeg = jbk_lo * kNb;
+    for (int jbk = jbk_lo; jbk < jbk_hi; jbk++) {
         const int jb = jbk * kNb, nbc = min(kNb, P - jb);
         int rb = jbk + ((warp - jbk) % kNW + kNW) % kNW;     // first owned row block >= jbk
         bool d_ready = false;
@@ -999,7 +1164,7 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
 #pragma unroll
                     for (int b = 0; b < 2; b++)
                         wr[a][b][0] = wr[a][b][1] = wi[a][b][0] = wi[a][b][1] = wx[a][b][0] = wx[a][b][1] = 0.0;
-                if (jb > 0) {
+                if (jb > kbeg) {
                     const double2* arow[2];
                     const double2* brow[2];
 #pragma unroll
@@ -1043,8 +1208,8 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
 #pragma unroll
                             for (int s2 = 0; s2 < 2; s2++) { sa[q][s2] = arow[s2][k0 + 4 * q]; sb[q][s2] = brow[s2][k0 + 4 * q]; }
                     };
-                    load2(pa, pb, 0);
-                    for (int k0 = 0; k0 < jb; k0 += 16) {
+                    load2(pa, pb, kbeg);
+                    for (int k0 = kbeg; k0 < jb; k0 += 16) {
                         load2(qa, qb, k0 + 8);
                         kstep(pa[0], pb[0]); kstep(pa[1], pb[1]);
                         if (k0 + 16 < jb) load2(pa, pb, k0 + 16);
@@ -1146,6 +1311,7 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
         TMARK(5);           // wait end of block column
     }
 
+    if (jbk_hi < ncb) return;                         // more panels to come
     // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y.
     // Per block column (last to first): the diagonal block is brought into shared memory with one coalesced load
     // (the 16 dependent steps of the triangular solve then never touch global memory), the contribution of the
@@ -1543,6 +1709,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
         CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
         CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdSmem));
     }
     // experiment knob (tools only): EAQHM_GRAM_VARIANT=1 selects the CTA-tiled kernel, 3 the warp kernel with four real
     // products per complex product; default: warp kernel with three (3M)
@@ -1566,10 +1734,31 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
     CHECK_ARG(xs_bytes - pad <= 32 * 1024);
-    if (warps == 1) LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a));
-    else if (warps == 4) LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a));
-    else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a));
-    else LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a));
+    // experiment knobs (tools only): EAQHM_CHOL_PANEL=1 selects the two-level (panel) factorisation; EAQHM_CHOL_UPD_3M=0
+    // forms the panel update's complex products from four real products
+    static const bool panels = getenv("EAQHM_CHOL_PANEL") && atoi(getenv("EAQHM_CHOL_PANEL")) != 0;
+    static const bool upd3m = !(getenv("EAQHM_CHOL_UPD_3M") && atoi(getenv("EAQHM_CHOL_UPD_3M")) == 0);
+    if (panels && warps == 2 && a.Pmax > kPanelW) {
+        const int np = (a.Pmax + kPanelW - 1) / kPanelW;
+        const int nrbmax = (a.Pmax + 1 + kNb - 1) / kNb;
+        const int nsm = eaqhm_sm_count();
+        for (int J = 0; J < np; J++) {
+            if (J > 0) {
+                const int ipf = nrbmax - J * (kPanelW / kNb);
+                const long long nitems = (long long)a.nf * ipf;
+                int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
+                if ((long long)blocks * kUWarps > nitems) blocks = (int)((nitems + kUWarps - 1) / kUWarps);
+                if (upd3m) LAUNCH(KC_CHOL_UPDATE, st, k_chol_update<true><<<blocks, kUWarps * 32, kUpdSmem, st>>>(a, J, ipf));
+                else LAUNCH(KC_CHOL_UPDATE, st, k_chol_update<false><<<blocks, kUWarps * 32, kUpdSmem, st>>>(a, J, ipf));
+            }
+            LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a, J));
+        }
+        return EAQHM_OK;
+    }
+    if (warps == 1) LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a, -1));
+    else if (warps == 4) LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a, -1));
+    else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a, -1));
+    else LAUNCH(KC_CHOL, st, k_chol_solve<2><<<a.nf, 64, xs_bytes, st>>>(a, -1));
     return EAQHM_OK;
 }
 

@@ -131,6 +131,21 @@ class BufferPool:
 _PINNED = {}
 
 
+_COPY_POOL = None
+
+
+def _parallel_copies(views):
+    """Pageable copies of pinned staging views on a few host threads (numpy releases the GIL for large copies): the
+    result arrays own their memory, the staging buffers are reused by the next call."""
+    global _COPY_POOL
+    if sum(v.nbytes for v in views) < (4 << 20):
+        return [v.copy() for v in views]
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=4)
+    return list(_COPY_POOL.map(np.copy, views))
+
+
 def _to_host(t, tag):
     """Device tensor -> numpy through a cached pinned staging buffer (grow-only, one per tag)."""
     n = t.numel()
@@ -283,6 +298,10 @@ class Engine:
         self.h2d_bytes = _h2d_counter[0]
         self.d2h_bytes = 0
         self.useful_flops = dict(gram=0.0, chol=0.0, basis=0.0)
+        # read-back of the best snapshot overlapped with the next adaptation (run(): copy stream + pinned staging)
+        self._copy_stream = None
+        self._copy_done = None
+        self._views = None
 
     # ------------------------------------------------------------------------------
     def _stream(self):
@@ -352,7 +371,23 @@ class Engine:
         with np.errstate(all="ignore"):
             return 20 * np.log10(self.std_det / np.sqrt(stat[self.U:] / self.stat_n))
 
+    def _start_readback(self):
+        """Device -> pinned host copy of the current best snapshot on the copy stream, ordered after everything queued on
+        the main stream so far; the loop goes on meanwhile.  The next snapshot waits for it (it rewrites the source)."""
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            self._views = [_to_host(self.s_best, "s")] + [_to_host(x, "k%d" % i) for i, x in enumerate(self.best)]
+            self._copy_done = torch.cuda.Event()
+            self._copy_done.record(self._copy_stream)
+
     def snapshot(self, improved):
+        if self._copy_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._copy_done)
         self.improved.copy_(torch.from_numpy(np.asarray(improved, bool).astype(np.uint8)))
         with torch.cuda.device(self.device):
             self._snapshot()
@@ -364,17 +399,23 @@ class Engine:
                                          self._stream()))
 
     # ------------------------------------------------------------------------------
-    def run_device(self, on_adaptation=None):
+    def run_device(self, on_adaptation=None, fixed_adaptations=None, prefetch_results=False):
         """The adaptation loop (functions.py:163-402) on the resident inputs; results stay on the device.
-        Returns (SRER per utterance, index of the best adaptation per utterance, frame solves)."""
+        Returns (SRER per utterance, index of the best adaptation per utterance, frame solves).
+        fixed_adaptations (benchmark mode): exactly that many adaptations for every utterance, no convergence stop;
+        the snapshot still ends at the adaptation the reference would return.
+        prefetch_results: start the device -> host copy of the snapshot after every improving adaptation, hidden behind
+        the next adaptation's kernels (run() does; results() then only waits for the last copy)."""
         U = self.U
+        self._copy_done = self._views = None
         active = np.ones(U, bool)
+        stopped = np.zeros(U, bool)
         SRER = [[] for _ in range(U)]
         best_a = np.zeros(U, int)
         frames_solved = 0
         self.status.zero_()
         self.flops.zero_()
-        for a in range(self.maxAdpt + 1):
+        for a in range(self.maxAdpt + 1 if fixed_adaptations is None else int(fixed_adaptations)):
             nA = self.set_active(active)
             frames_solved += nA
             self.analysis(a)
@@ -388,11 +429,16 @@ class Engine:
                     srer = srer_u[u]
                     SRER[u].append(srer)
                     if a != 0 and srer <= SRER[u][a - 1]:                   # functions.py:394-396
-                        active[u] = False
+                        stopped[u] = True
+                        active[u] = fixed_adaptations is not None
+                    if stopped[u]:
+                        pass
                     else:
                         improved[u] = True
                         best_a[u] = a
             self.snapshot(improved)                                         # functions.py:397-402
+            if prefetch_results and improved.any():
+                self._start_readback()
             self.h2d_bytes += U
             if on_adaptation is not None:
                 on_adaptation(a, SRER)
@@ -405,12 +451,17 @@ class Engine:
 
     def run(self, on_adaptation=None):
         """Adaptation loop + copy of the results to host arrays.  Returns one Result per utterance."""
-        return self.results(*self.run_device(on_adaptation))
+        return self.results(*self.run_device(on_adaptation, prefetch_results=True))
 
     def results(self, SRER, best_a, frames_solved=0):
         K, G = self.Kmax, self.G
-        views = [_to_host(self.s_best, "s")] + [_to_host(x, "k%d" % i) for i, x in enumerate(self.best)]
-        status = self.status.cpu().numpy()                                          # synchronises the copies above
+        status = self.status.cpu().numpy()
+        # a prefetched copy is the final snapshot unless the 140 Hz fallback wrote its in-place amplitude into it
+        # afterwards (Q10: the write of adaptation a+1 lands in the snapshot of adaptation a)
+        if self._copy_done is None or status[1] > 0:
+            self._start_readback()
+        self._copy_done.synchronize()
+        views, self._copy_done, self._views = self._views, None, None
         s_best = views[0].numpy()
         b_am, b_ph, b_fm = [v.numpy().reshape(G, K) for v in views[1:4]]            # frame-major snapshot
         b_a0 = views[4].numpy()
@@ -420,10 +471,11 @@ class Engine:
             g0, n = self.gfirst[i], f.No_ti
             sl = slice(g0, g0 + n)
             ku = u.Kmax
+            s_u, a0_u, am_u, fm_u, ph_u = _parallel_copies([s_best[self.ustart[i]:self.ustart[i] + f.length], b_a0[sl],
+                                                            b_am[sl, :ku], b_fm[sl, :ku], b_ph[sl, :ku]])
             out.append(Result(
-                s_recon=s_best[self.ustart[i]:self.ustart[i] + f.length].copy(), SRER=list(SRER[i]), ti=f.ti0.copy(),
-                isSpeech=f.isSpeech.copy(), isVoiced=f.analysed.copy(), a0=b_a0[sl].copy(),
-                am=b_am[sl, :ku].copy(), fm=b_fm[sl, :ku].copy(), ph=b_ph[sl, :ku].copy(),
+                s_recon=s_u, SRER=list(SRER[i]), ti=f.ti0.copy(),
+                isSpeech=f.isSpeech.copy(), isVoiced=f.analysed.copy(), a0=a0_u, am=am_u, fm=fm_u, ph=ph_u,
                 n_adapt_best=int(best_a[i]), fs=int(self.fs), step=self.step,
                 stats=dict(not_pd_frames=int(status[0]), fallback_frames=int(status[1]),
                            frames_solved=int(frames_solved))))

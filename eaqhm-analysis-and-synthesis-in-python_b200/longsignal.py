@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import BufferPool, Engine, Result, Utterance, _to_host, check_not_pd, merge_stats
+from .engine import BufferPool, Engine, Result, Utterance, _parallel_copies, _to_host, check_not_pd, merge_stats
 from .host import FrameTables
 from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks
 
@@ -175,6 +175,7 @@ class LongSignalEngine:
                                     n_stat=float(own_hi - own_lo)))
             self.h2d_bytes += e.h2d_bytes
         self.tracks_hold = None          # (shard index, adaptation) whose tracks the pool currently holds
+        self._copy_stream = self._copy_done = self._copy_prev = self._views = None
         self.exchanged_bytes = 0
         self.frames_owned = int(sum(len(sh["eng"].alists[0]) for sh in self.shards))
 
@@ -199,9 +200,30 @@ class LongSignalEngine:
         # Q10 (functions.py:210,383,400): the fallback's in-place amplitude lands in the rows of the best store
         return self.best[0].data_ptr() + sh["r0"] * self.Kmax * 8
 
-    def run_device(self, on_adaptation=None):
-        """Adaptation loop; results stay on the device.  Returns (SRER list, best adaptation, frame solves)."""
+    def _start_readback(self):
+        """Device -> pinned host copy of the owned part of the best store and waveform on the copy stream, ordered
+        after everything queued so far; the next adaptation runs meanwhile (it writes the OTHER store)."""
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        o0, o1 = self.F_lo - self.S_lo, self.F_hi - self.S_lo
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            self._views = [_to_host(self.s_best, "ls")] + [_to_host(x[o0:o1], "lk%d" % i) for i, x in enumerate(self.best)]
+            self._copy_prev, self._copy_done = self._copy_done, torch.cuda.Event()
+            self._copy_done.record(self._copy_stream)
+
+    def run_device(self, on_adaptation=None, fixed_adaptations=None, prefetch_results=False):
+        """Adaptation loop; results stay on the device.  Returns (SRER list, best adaptation, frame solves).
+        fixed_adaptations (benchmark mode): exactly that many adaptations, no convergence stop (the best store still
+        ends at the adaptation the reference would return), so that runs on different ranges do the same work.
+        prefetch_results: copy the best store to the host after every improving adaptation, hidden behind the next
+        adaptation (run() does; results() then only waits for the last copy)."""
         SRER, best_a, solves = [], 0, 0
+        stopped = False
+        self._copy_done = self._copy_prev = self._views = None
         ones = np.ones(1, bool)
         nsh = len(self.shards)
         stat_dev = torch.zeros((nsh, 2), dtype=torch.float64, device=self.device)
@@ -212,7 +234,7 @@ class LongSignalEngine:
         self.pool.get("flops", 3, torch.float64).zero_()
         self.exchanged_bytes = 0
         self.tracks_hold = None
-        for a in range(self.maxAdpt + 1):
+        for a in range(self.maxAdpt + 1 if fixed_adaptations is None else int(fixed_adaptations)):
             # ---- pass 1: analysis of adaptation a on the tracks of adaptation a-1 -----------------------------
             order = list(range(nsh))
             if self.tracks_hold is not None and self.tracks_hold[1] == a - 1:
@@ -233,6 +255,8 @@ class LongSignalEngine:
             self.exchanged_bytes += exchange_halo_rows(self.new, (self.F_lo - self.S_lo, self.F_hi - self.S_lo),
                                                        self.H, self.rank, self.world, self.dist)
             # ---- pass 2: tracks of adaptation a, resynthesis, statistics, candidate snapshot --------------------
+            if self._copy_prev is not None:          # the candidate store was the best store two copies ago
+                torch.cuda.current_stream(self.device).wait_event(self._copy_prev)
             for j in range(nsh):
                 sh = self.shards[j]
                 e = sh["eng"]
@@ -258,11 +282,17 @@ class LongSignalEngine:
             if on_adaptation is not None:
                 on_adaptation(a, SRER)
             if a != 0 and srer <= SRER[a - 1]:                                 # functions.py:394-396
-                break
+                if fixed_adaptations is None:
+                    break
+                stopped = True
+            self.cur, self.new = self.new, self.cur
+            if stopped:
+                continue
             self.best, self.cand = self.cand, self.best                       # functions.py:397-402
             self.s_best, self.s_hat = self.s_hat, self.s_best
-            self.cur, self.new = self.new, self.cur
             best_a = a
+            if prefetch_results:
+                self._start_readback()
         fl = self.pool.get("flops", 3, torch.float64).cpu().numpy()
         self.useful_flops = dict(gram=float(fl[0]), chol=float(fl[1]), basis=float(fl[2]))
         check_not_pd(int(self.pool.get("status", 2, torch.int32)[0].item()))
@@ -271,15 +301,17 @@ class LongSignalEngine:
     def results(self, SRER, best_a, solves=0):
         """Owned part of the result as host arrays inside a full-length Result (zeros outside this rank's range)."""
         full, K = self.full, self.Kmax
-        o0, o1 = self.F_lo - self.S_lo, self.F_hi - self.S_lo
-        views = [_to_host(self.s_best, "ls")] + [_to_host(x[o0:o1], "lk%d" % i) for i, x in enumerate(self.best)]
         status = self.pool.get("status", 2, torch.int32).cpu().numpy()
+        # a prefetched copy is final unless the 140 Hz fallback wrote into the best store afterwards (Q10)
+        if self._copy_done is None or status[1] > 0:
+            self._start_readback()
+        self._copy_done.synchronize()
+        views, self._copy_done, self._copy_prev, self._views = self._views, None, None, None
         n = self.F_hi - self.F_lo
         if self.world == 1:
             # the rank owns the whole signal: one copy out of the pinned staging buffers
-            s_recon = views[0].numpy().copy()
-            am, ph, fm = (views[i].numpy().reshape(n, K).copy() for i in (1, 2, 3))
-            a0 = views[4].numpy().copy()
+            s_recon, am, ph, fm, a0 = _parallel_copies([views[0].numpy()] + [views[i].numpy().reshape(n, K) for i in (1, 2, 3)]
+                                                       + [views[4].numpy()])
         else:
             s_recon = np.zeros(full.length)
             s_recon[self.R_lo:self.R_hi] = views[0].numpy()
@@ -297,8 +329,8 @@ class LongSignalEngine:
                                  fallback_flags=int(status[1]), exchanged_bytes=int(self.exchanged_bytes),
                                  owned_samples=(self.R_lo, self.R_hi), owned_frames=(self.F_lo, self.F_hi)))
 
-    def run(self, on_adaptation=None):
-        return self.results(*self.run_device(on_adaptation))
+    def run(self, on_adaptation=None, fixed_adaptations=None):
+        return self.results(*self.run_device(on_adaptation, fixed_adaptations, prefetch_results=True))
 
 
 def analyze_long_signal(s, fs, f0s, voiced5, frame_step, f0min, Kmax, shard_seconds=20.0, det_part=None, step=15,

@@ -205,13 +205,17 @@ def frame_gate(length, step, analysisWindow, voiced5, frame_step):
 
 def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAdpt=10,
                  pitchPeriods=3, analysisWindow=32, det_part=None, keep_per_adapt=False,
-                 progress=None):
+                 progress=None, fixed_adaptations=None):
     """Restatement of functions.py:148-411.
 
     s (length,) float64 in [-1,1); f0s (n5,3) rows [t,f0,strength] on the 5 ms grid
     (functions.py:113); voiced5 (n5',) bool isVoiced flag per 5 ms frame AFTER the
     full-waveform override (functions.py:140-145); det_part = SRER target
     (functions.py:138,146; default s).
+
+    fixed_adaptations (benchmark mode, not in the reference): run exactly that many adaptations without the
+    convergence stop of functions.py:394-396, so that two sides do the same work; the returned result is still the
+    adaptation the reference would have returned (the last one before the first non-improvement).
     """
     s = np.asarray(s, float).reshape(-1)
     length = len(s)
@@ -230,7 +234,8 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
     frames_idx = np.flatnonzero(analysed)
     n_fallback = 0
 
-    for a in range(maxAdpt + 1):
+    stopped = False
+    for a in range(maxAdpt + 1 if fixed_adaptations is None else int(fixed_adaptations)):
         a0_recon = np.zeros(length)
         am_recon = np.zeros((length, Kmax))
         fm_recon = np.zeros((length, Kmax))
@@ -331,7 +336,11 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
                                   fm=fm_recon[c_all].copy(), ph=ph_recon[c_all].copy(),
                                   s=s_tmp.copy()))
         if a != 0 and SRER[a] <= SRER[a - 1]:                                       # :394-396
-            break
+            if fixed_adaptations is None:
+                break
+            stopped = True
+        if stopped:
+            continue
         best = (s_tmp.copy(), a0_dense, am_recon, fm_recon, ph_recon, a)            # :397-402 (am_fin aliases am_recon)
 
     s_recon, a0_fin, am_fin, fm_fin, pm_fin, a_best = best
