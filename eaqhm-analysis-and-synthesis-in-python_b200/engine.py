@@ -146,6 +146,15 @@ def _parallel_copies(views):
     return list(_COPY_POOL.map(np.copy, views))
 
 
+def _parallel_fill(pairs):
+    """dst[...] = src for (dst view, src view) pairs on the host copy threads (results of a rank inside full-length arrays)."""
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=4)
+    list(_COPY_POOL.map(lambda p: np.copyto(p[0], p[1]), pairs))
+
+
 def _to_host(t, tag):
     """Device tensor -> numpy through a cached pinned staging buffer (grow-only, one per tag)."""
     n = t.numel()

@@ -61,49 +61,80 @@ def voiced_only_target(s, speech5, voiced5, frame_step):
 
 
 class FrameTables:
-    """Per-frame quantities of one utterance (functions.py:148-157,176-194)."""
+    """Per-frame quantities of one utterance (functions.py:148-157,176-194).
+
+    frame_range=(g_lo, g_hi) limits the per-frame arrays to that range of the signal's frames (a rank of a multi-GPU
+    long-signal run only builds the tables of the range it touches); `g_base` is the signal frame index of array
+    element 0, `No_ti_total` the frame count of the whole signal, `No_ti` the number of frames the arrays cover."""
+
+    @staticmethod
+    def _values(ti, length, fs, f0s, voiced5, frame_step, Kmax, step, pitchPeriods, analysisWindow):
+        Fmax = int(fs / 2 - 200)
+        framei = ti / frame_step                                          # functions.py:155
+        fi = framei.astype(int)
+        dec = framei - fi
+        aw = analysisWindow * step
+        isSpeech = (ti > aw) & (ti < length - aw)                         # functions.py:180
+        nv = len(voiced5)
+        analysed = isSpeech & voiced5[(fi - 1) % nv] & voiced5[np.minimum(fi, nv - 1)]   # :181
+        idx = np.flatnonzero(analysed)
+        f0v = np.zeros(len(ti))
+        K0 = np.zeros(len(ti), np.int32)
+        N = np.zeros(len(ti), np.int32)
+        if len(idx):
+            f0 = (1 - dec[idx]) * f0s[fi[idx] - 1, 1] + dec[idx] * f0s[fi[idx], 1]      # functions.py:185
+            if not np.all(np.isfinite(f0)) or np.any(f0 <= 0):
+                raise ValueError("f0 track has non-finite or non-positive values on analysed frames")
+            f0v[idx] = f0
+            K0[idx] = np.minimum(Kmax, (Fmax / f0).astype(int))                    # functions.py:187
+            N[idx] = np.maximum(120, np.rint((pitchPeriods / 2) * (fs / f0))).astype(np.int32)   # :191
+            c = ti[idx] - 1
+            if np.any(c + N[idx] >= length):
+                raise IndexError("analysis window runs past the end of the signal "
+                                 "(the reference raises IndexError at functions.py:196)")
+            if np.any(K0[idx] < 1):
+                raise ValueError("f0 above Fmax: no harmonic fits")
+        return isSpeech, analysed, f0v, K0, N
 
     def __init__(self, length, fs, f0s, voiced5, frame_step, Kmax, step=15, pitchPeriods=3,
-                 analysisWindow=32):
+                 analysisWindow=32, frame_range=None):
         if analysisWindow * step < 2 * step:
             raise ValueError("analysisWindow*step must be at least 2*step (the reference's run detection "
                              "and short-run spline assume no frame is analysed at samples 0 and step)")
         f0s = np.asarray(f0s, float)
         voiced5 = np.asarray(voiced5, bool)
         self.length, self.step = int(length), int(step)
-        Fmax = int(fs / 2 - 200)
-        ti = np.arange(1, length, step)                                   # functions.py:148 (1-based)
-        self.No_ti = len(ti)
-        if self.No_ti < 4:
+        total = len(range(1, self.length, self.step))                     # functions.py:148: ti = arange(1, length, step)
+        if total < 4:
             raise ValueError("signal too short: the DC cubic spline needs at least 4 frames (functions.py:340)")
-        framei = ti / frame_step                                          # functions.py:155
-        fi = framei.astype(int)
-        dec = framei - fi
-        aw = analysisWindow * step
-        self.isSpeech = (ti > aw) & (ti < length - aw)                    # functions.py:180
-        nv = len(voiced5)
-        self.analysed = self.isSpeech & voiced5[(fi - 1) % nv] & voiced5[np.minimum(fi, nv - 1)]   # :181
-        idx = np.flatnonzero(self.analysed)
-        self.f0 = np.zeros(self.No_ti)
-        self.K0 = np.zeros(self.No_ti, np.int32)
-        self.N = np.zeros(self.No_ti, np.int32)
-        if len(idx):
-            f0 = (1 - dec[idx]) * f0s[fi[idx] - 1, 1] + dec[idx] * f0s[fi[idx], 1]      # functions.py:185
-            if not np.all(np.isfinite(f0)) or np.any(f0 <= 0):
-                raise ValueError("f0 track has non-finite or non-positive values on analysed frames")
-            self.f0[idx] = f0
-            self.K0[idx] = np.minimum(Kmax, (Fmax / f0).astype(int))                    # functions.py:187
-            self.N[idx] = np.maximum(120, np.rint((pitchPeriods / 2) * (fs / f0))).astype(np.int32)   # :191
-            c = ti[idx] - 1
-            if np.any(c + self.N[idx] >= length):
-                raise IndexError("analysis window runs past the end of the signal "
-                                 "(the reference raises IndexError at functions.py:196)")
-            if np.any(self.K0[idx] < 1):
-                raise ValueError("f0 above Fmax: no harmonic fits")
+        g_lo, g_hi = (0, total) if frame_range is None else (max(0, int(frame_range[0])), min(total, int(frame_range[1])))
+        self.No_ti_total, self.g_base, self.No_ti = total, g_lo, g_hi - g_lo
+        args = (self.length, fs, f0s, voiced5, frame_step, Kmax, step, pitchPeriods, analysisWindow)
+        ti = 1 + self.step * np.arange(g_lo, g_hi, dtype=np.int64)        # 1-based centres
+        self.isSpeech, self.analysed, self.f0, self.K0, self.N = self._values(ti, *args)
         self.ti0 = ti - 1                                                 # 0-based centres (functions.py:325)
-        self.f0stale = float(self.f0[idx[-1]]) if len(idx) else 0.0       # quirk Q1
+        # quirk Q1: f0 of the LAST analysed frame of the whole signal; a range that stops short of the signal's end
+        # looks for it from the end in blocks
+        self.f0stale = 0.0
+        idx = np.flatnonzero(self.analysed)
+        if g_hi == total and len(idx):
+            self.f0stale = float(self.f0[idx[-1]])
+        else:
+            hi = total
+            while hi > 0:
+                lo = max(0, hi - 4096)
+                if lo >= g_lo and hi <= g_hi:
+                    an, f0b = self.analysed[lo - g_lo:hi - g_lo], self.f0[lo - g_lo:hi - g_lo]
+                else:
+                    _, an, f0b, _, _ = self._values(1 + self.step * np.arange(lo, hi, dtype=np.int64), *args)
+                j = np.flatnonzero(an)
+                if len(j):
+                    self.f0stale = float(f0b[j[-1]])
+                    break
+                hi = lo
         self.own = np.full(self.No_ti, step, np.int32)
-        self.own[-1] = length - self.ti0[-1]
+        if g_hi == total:
+            self.own[-1] = length - self.ti0[-1]
 
     def wrapping_frames(self):
         """Analysed frames whose window starts before sample 0: the reference's fancy index wraps those samples to
@@ -123,10 +154,13 @@ class FrameTables:
         e.length, e.step = int(hi - lo), self.step
         g0 = lo // self.step
         n = len(np.arange(1, e.length, self.step))
-        if n < 4 or g0 + n > self.No_ti:
+        if n < 4 or g0 + n > self.No_ti_total:
             raise ValueError("excerpt too short or off the frame grid")
+        if g0 < self.g_base or g0 + n > self.g_base + self.No_ti:
+            raise ValueError("excerpt outside the frame range these tables were built for")
         e.No_ti, e.g0 = n, int(g0)
-        sl = slice(g0, g0 + n)
+        e.No_ti_total, e.g_base = n, 0
+        sl = slice(g0 - self.g_base, g0 - self.g_base + n)
         e.isSpeech, e.analysed = self.isSpeech[sl].copy(), self.analysed[sl].copy()
         e.f0, e.K0, e.N = self.f0[sl].copy(), self.K0[sl].copy(), self.N[sl].copy()
         e.ti0 = self.ti0[sl] - lo

@@ -25,7 +25,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import BufferPool, Engine, Result, Utterance, _parallel_copies, _to_host, check_not_pd, merge_stats
+from .engine import (BufferPool, Engine, Result, Utterance, _parallel_copies, _parallel_fill, _to_host, check_not_pd,
+                     merge_stats)
 from .host import FrameTables
 from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks
 
@@ -120,35 +121,69 @@ class LongSignalEngine:
         self.fs, self.step, self.maxAdpt, self.Kmax = fs, int(step), int(maxAdpt), int(Kmax)
         s = np.asarray(s, float).reshape(-1)
         det = s if det_part is None else np.asarray(det_part, float).reshape(-1)
-        self.full = full_tables if full_tables is not None else FrameTables(
-            len(s), fs, f0s, voiced5, frame_step, Kmax, step, pitchPeriods, analysisWindow)
-        full = self.full
-        if len(full.wrapping_frames()):
-            raise ValueError("%d analysed frame(s) have a window that starts before sample 0 (the reference wraps it to "
-                             "the end of the signal): not supported by the frame-range engine; use engine.Engine, or "
-                             "raise analysisWindow so that analysisWindow*step >= the largest half window (%d samples)"
-                             % (len(full.wrapping_frames()), int(full.N.max())))
+        length, total = len(s), len(range(1, len(s), self.step))
+        # Everything a rank sets up is local to its range: the halo follows from a bound on the half window that every
+        # rank derives alike from the f0 grid (the f0 of a frame is a convex combination of two voiced grid values,
+        # functions.py:185), the per-frame tables cover the rank's frames only, the target's standard deviation comes
+        # from per-shard sums exchanged below.
+        f0g = np.asarray(f0s, float)[:, 1]
+        m = min(len(f0g), len(voiced5))
+        vg = f0g[:m][np.asarray(voiced5, bool)[:m] & np.isfinite(f0g[:m]) & (f0g[:m] > 0)]
+        N_bound = int(max(120, np.rint((pitchPeriods / 2) * (fs / vg.min())))) if len(vg) else 120     # functions.py:191
+        if full_tables is not None:
+            N_bound = int(full_tables.N.max())
         align = int(np.lcm(self.step, int(frame_step)))
-        self.halo = exchange_halo_samples(int(full.N.max()), self.step, analysisWindow, align)
+        self.halo = exchange_halo_samples(N_bound, self.step, analysisWindow, align)
         self.H = self.halo // self.step
-        self.plan_all = plan_ranges(full.length, int(shard_seconds * fs), self.halo, align, self.world)
+        self.plan_all = plan_ranges(length, int(shard_seconds * fs), self.halo, align, self.world)
         self.plan = self.plan_all[self.rank]
         self.R_lo, self.R_hi = self.plan[0][0], self.plan[-1][1]
         cdiv = lambda a, b: -(-a // b)
-        self.F_lo, self.F_hi = cdiv(self.R_lo, self.step), min(full.No_ti, cdiv(self.R_hi, self.step))
-        if self.world > 1 and self.F_hi - self.F_lo < self.H:
-            raise ValueError("a rank must own at least the halo (%d frames)" % self.H)
-        self.S_lo, self.S_hi = max(0, self.F_lo - self.H), min(full.No_ti, self.F_hi + self.H)
+        self.F_lo, self.F_hi = cdiv(self.R_lo, self.step), min(total, cdiv(self.R_hi, self.step))
+        self.S_lo, self.S_hi = max(0, self.F_lo - self.H), min(total, self.F_hi + self.H)
+        self.X_lo, self.X_hi = self.plan[0][2], self.plan[-1][3]          # resident samples: owned range + halo
+        # frames of the resident samples (a superset of the store rows: the excerpt tables are sliced from these)
+        err = None
+        try:
+            if self.world > 1 and self.F_hi - self.F_lo < self.H:
+                raise ValueError("a rank must own at least the halo (%d frames)" % self.H)
+            self.full = full_tables if full_tables is not None else FrameTables(
+                length, fs, f0s, voiced5, frame_step, Kmax, step, pitchPeriods, analysisWindow,
+                frame_range=(self.X_lo // self.step, cdiv(self.X_hi, self.step)))
+            if len(self.full.wrapping_frames()):
+                raise ValueError("%d analysed frame(s) have a window that starts before sample 0 (the reference wraps it "
+                                 "to the end of the signal): not supported by the frame-range engine; use engine.Engine, or "
+                                 "raise analysisWindow so that analysisWindow*step >= the largest half window (%d samples)"
+                                 % (len(self.full.wrapping_frames()), int(self.full.N.max())))
+        except (ValueError, IndexError) as e:
+            err = e
+        if self.world > 1:
+            # an input error on one rank (window past the end of the signal: the last rank only) must stop all of them
+            flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if err is None and int(flag.item()):
+                err = ValueError("another rank rejected its range of the signal")
+        if err is not None:
+            raise err
+        full = self.full
         rows = self.S_hi - self.S_lo
         d, K = self.device, self.Kmax
-        # resident signal of this rank: owned range + halo
-        self.X_lo, self.X_hi = self.plan[0][2], self.plan[-1][3]
         self.h2d_bytes = 2 * (self.X_hi - self.X_lo) * 8
         self.d2h_bytes = 0
         self.s_dev = torch.from_numpy(np.ascontiguousarray(s[self.X_lo:self.X_hi])).to(d)
         self.det_dev = self.s_dev if det_part is None else torch.from_numpy(
             np.ascontiguousarray(det[self.X_lo:self.X_hi])).to(d)
-        self.std_det = float(np.std(det))                                    # functions.py:161
+        # functions.py:161: population standard deviation of the whole target, from (n, mean, M2) of every shard's owned
+        # samples merged in shard order (the same arithmetic whatever the number of ranks)
+        nmax = max(len(p) for p in self.plan_all)
+        st = np.zeros((nmax, 3))
+        for j, (own_lo, own_hi, _, _) in enumerate(self.plan):
+            x = det[own_lo:own_hi]
+            mu = x.mean()
+            st[j] = (own_hi - own_lo, mu, ((x - mu) ** 2).sum())
+        st = allgather_rows(torch.from_numpy(st).to(d), self.world, self.dist).cpu().numpy()
+        n_all, _, m2_all = merge_stats([("t", r[0], r[1], r[2]) for r in st if r[0] > 0])["t"]
+        self.std_det = float(np.sqrt(m2_all / n_all))
         f64 = dict(dtype=torch.float64, device=d)
 
         def store():
@@ -168,7 +203,7 @@ class LongSignalEngine:
             e = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow,
                        device=d, frame_tables=[ft], pool=self.pool, **engine_kw)
             e.set_active([True])
-            g_lo, g_hi = cdiv(own_lo, self.step), min(full.No_ti, cdiv(own_hi, self.step))
+            g_lo, g_hi = cdiv(own_lo, self.step), min(full.No_ti_total, cdiv(own_hi, self.step))
             self.shards.append(dict(eng=e, ft=ft, own=(own_lo, own_hi), ex=(ex_lo, ex_hi),
                                     r0=ft.g0 - self.S_lo,                     # store row of the excerpt's first frame
                                     l0=g_lo - ft.g0, l1=g_hi - ft.g0,         # owned frames, excerpt-local
@@ -314,16 +349,20 @@ class LongSignalEngine:
                                                        + [views[4].numpy()])
         else:
             s_recon = np.zeros(full.length)
-            s_recon[self.R_lo:self.R_hi] = views[0].numpy()
-            am, fm, ph = (np.zeros((full.No_ti, K)) for _ in range(3))
-            a0 = np.zeros(full.No_ti)
-            am[self.F_lo:self.F_hi] = views[1].numpy().reshape(n, K)
-            ph[self.F_lo:self.F_hi] = views[2].numpy().reshape(n, K)
-            fm[self.F_lo:self.F_hi] = views[3].numpy().reshape(n, K)
-            a0[self.F_lo:self.F_hi] = views[4].numpy()
+            am, fm, ph = (np.zeros((full.No_ti_total, K)) for _ in range(3))
+            a0 = np.zeros(full.No_ti_total)
+            fr = slice(self.F_lo, self.F_hi)
+            _parallel_fill([(s_recon[self.R_lo:self.R_hi], views[0].numpy()), (am[fr], views[1].numpy().reshape(n, K)),
+                            (ph[fr], views[2].numpy().reshape(n, K)), (fm[fr], views[3].numpy().reshape(n, K)),
+                            (a0[fr], views[4].numpy())])
         self.d2h_bytes += (self.R_hi - self.R_lo) * 8 + n * (3 * K + 1) * 8
-        return Result(s_recon=s_recon, SRER=list(SRER), ti=full.ti0.copy(), isSpeech=full.isSpeech.copy(),
-                      isVoiced=full.analysed.copy(), a0=a0, am=am, fm=fm, ph=ph, n_adapt_best=int(best_a),
+        # flags of the owned frames inside full-length arrays (like the parameters: zeros outside this rank's range)
+        T, b = full.No_ti_total, full.g_base
+        speech, voiced = np.zeros(T, bool), np.zeros(T, bool)
+        speech[self.F_lo:self.F_hi] = full.isSpeech[self.F_lo - b:self.F_hi - b]
+        voiced[self.F_lo:self.F_hi] = full.analysed[self.F_lo - b:self.F_hi - b]
+        return Result(s_recon=s_recon, SRER=list(SRER), ti=self.step * np.arange(T, dtype=np.int64), isSpeech=speech,
+                      isVoiced=voiced, a0=a0, am=am, fm=fm, ph=ph, n_adapt_best=int(best_a),
                       fs=int(self.fs), step=self.step,
                       stats=dict(shards=len(self.shards), frames_solved=int(solves), not_pd_frames=int(status[0]),
                                  fallback_flags=int(status[1]), exchanged_bytes=int(self.exchanged_bytes),

@@ -65,7 +65,8 @@ def _bare_tables(length, step):
     ft.length, ft.step = int(length), int(step)
     ti = np.arange(1, length, step)
     n = len(ti)
-    ft.No_ti = n
+    ft.No_ti = ft.No_ti_total = n
+    ft.g_base = 0
     ft.isSpeech, ft.analysed = np.zeros(n, bool), np.zeros(n, bool)
     ft.f0, ft.K0, ft.N = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
     ft.ti0 = ti - 1

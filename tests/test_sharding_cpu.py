@@ -73,6 +73,35 @@ def test_excerpt_tables_are_slices_of_the_signal_tables():
         full.excerpt(7, 16000)
 
 
+def test_range_limited_tables_equal_the_signal_tables():
+    """A rank of a long-signal run builds the per-frame tables of its own frame range only (host.FrameTables
+    frame_range): same values as the slice of the whole signal's tables, the stale f0 of quirk Q1 found from the
+    signal's end, excerpts cut from them identical."""
+    fs, step, fstep = 16000, 15, 80
+    length = fs * 4 + 33
+    t5 = np.arange(0, length - 1, fstep) / fs
+    f0s = np.stack([t5, 140 + 30 * np.sin(2 * np.pi * 0.7 * t5), np.ones_like(t5)], axis=1)
+    voiced5 = np.ones(len(np.arange(1, length, fstep)), bool)
+    voiced5[300:420] = False
+    voiced5[-90:] = False                       # the last analysed frame lies well before the end (Q1 search)
+    full = engine.FrameTables(length, fs, f0s, voiced5, fstep, 70)
+    for g_lo, g_hi in ((0, 1500), (1200, 3000), (2900, full.No_ti), (-5, 10 ** 9)):
+        part = engine.FrameTables(length, fs, f0s, voiced5, fstep, 70, frame_range=(g_lo, g_hi))
+        a, b = max(0, g_lo), min(full.No_ti, g_hi)
+        assert part.g_base == a and part.No_ti == b - a and part.No_ti_total == full.No_ti
+        for name in ("f0", "K0", "N", "analysed", "isSpeech", "ti0", "own"):
+            assert (getattr(part, name) == getattr(full, name)[a:b]).all(), name
+        assert part.f0stale == full.f0stale and full.f0stale > 0
+    part = engine.FrameTables(length, fs, f0s, voiced5, fstep, 70, frame_range=(1200, 3000))
+    lo, hi = 1300 * step, 2800 * step
+    e1, e2 = full.excerpt(lo, hi), part.excerpt(lo, hi)
+    for name in ("f0", "K0", "N", "analysed", "isSpeech", "ti0", "own"):
+        assert (getattr(e1, name) == getattr(e2, name)).all()
+    assert e1.g0 == e2.g0 and e1.f0stale == e2.f0stale
+    with pytest.raises(ValueError):
+        part.excerpt(0, 16000)
+
+
 def test_merge_stats_equals_numpy_std():
     rng = np.random.default_rng(1)
     parts = [rng.standard_normal(n) * sc + off for n, sc, off in ((1000, 1.0, 0.1), (10, 3.0, -2.0), (5000, 0.2, 0.0))]
