@@ -80,6 +80,7 @@ class PathHandle:
         return r[0] if self.single else r
 
     def run(self, on_adaptation=None, fixed_adaptations=None):
+        self.eng.prepare_readback()
         return self.results(self.run_device(on_adaptation, fixed_adaptations, prefetch_results=True))
 
 

@@ -956,6 +956,7 @@ __global__ void __launch_bounds__(256) k_gram_toeplitz(AnaArgs A) {
 // dealt round-robin to a persistent grid.
 // ---------------------------------------------------------------------------------------
 constexpr int kPanelW = 48;                           // columns per panel (three 16-wide block columns)
+constexpr int kPanelMinP = 480;                       // systems at least this large take the panel factorisation
 constexpr int kUK = 8;                                // factor columns per pipeline stage
 constexpr int kUPitch = 12;                           // row pitch of a stage in double2: 8 + 4 pad = 192 B == 64 mod 128
 constexpr int kUStage = (16 + kPanelW) * kUPitch;     // double2 per stage: 16 A rows, then 48 B rows
@@ -968,13 +969,18 @@ __global__ void __launch_bounds__(kUWarps * 32, 2) k_chol_update(SolveArgs A, in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lr = lane >> 2, lc = lane & 3;
     double2* ring = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * 2 * kUStage;
-    const long long nitems = (long long)A.nf * items_per_frame;
-    const long long gw = (long long)blockIdx.x * kUWarps + warp, nw = (long long)gridDim.x * kUWarps;
+    const int nitems = A.nf * items_per_frame;
     const int Jb = panel * kPanelW, rt0 = Jb / kNb;
     const int Pp = A.Pp;
 
-    for (long long item = gw; item < nitems; item += nw) {
-        const int jl = (int)(item / items_per_frame), rt = rt0 + (int)(item - (long long)jl * items_per_frame);
+    // Work items (frame, row tile) come off one global queue: a static round-robin over 1,184 warps = 74 x 16 would hand
+    // a warp the same row tile of every frame whenever a frame has 16 items (profiles/r02_chol_experiments.md)
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(A.counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int jl = item / items_per_frame, rt = rt0 + (item - jl * items_per_frame);
         const int P = 2 * A.Mcols[jl] + 2 * A.dc;
         const int i0 = rt * kNb;
         if (i0 > P || Jb >= P) continue;              // past the rhs row / frame already factored
@@ -1697,6 +1703,7 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
     l.off_X = o;   o = align_up(o + (int64_t)chunk * 2 * l.Mxmax * l.Lp * 8, 256);
     l.off_R = o;   o = align_up(o + (int64_t)chunk * (l.Pmax + 1) * l.Pp * 16, 256);
     l.off_x = o;   o = align_up(o + (int64_t)chunk * l.Pmax * 16, 256);
+    l.off_cnt = o; o = align_up(o + 256, 256);
     l.total = o;
     return l;
 }
@@ -1734,9 +1741,12 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
     CHECK_ARG(xs_bytes - pad <= 32 * 1024);
-    // experiment knobs (tools only): EAQHM_CHOL_PANEL=1 selects the two-level (panel) factorisation; EAQHM_CHOL_UPD_3M=0
-    // forms the panel update's complex products from four real products
-    static const bool panels = getenv("EAQHM_CHOL_PANEL") && atoi(getenv("EAQHM_CHOL_PANEL")) != 0;
+    // Two-level (panel) factorisation for large systems: measured cross-over between P = 346 (single kernel 19 % faster)
+    // and P = 586 (panels 20 % faster; P = 1,186: 43 %), profiles/r02_chol_experiments.md.  Experiment knobs (tools only):
+    // EAQHM_CHOL_PANEL=0/1 forces one or the other; EAQHM_CHOL_UPD_3M=0 forms the panel update's complex products from
+    // four real products
+    static const int panel_env = getenv("EAQHM_CHOL_PANEL") ? atoi(getenv("EAQHM_CHOL_PANEL")) : -1;
+    const bool panels = panel_env >= 0 ? panel_env != 0 : a.Pmax >= kPanelMinP;
     static const bool upd3m = !(getenv("EAQHM_CHOL_UPD_3M") && atoi(getenv("EAQHM_CHOL_UPD_3M")) == 0);
     if (panels && warps == 2 && a.Pmax > kPanelW) {
         const int np = (a.Pmax + kPanelW - 1) / kPanelW;
@@ -1746,6 +1756,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
             if (J > 0) {
                 const int ipf = nrbmax - J * (kPanelW / kNb);
                 const long long nitems = (long long)a.nf * ipf;
+                CHECK_ARG(nitems < (1LL << 31) - 4096);
+                CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(int32_t), st));
                 int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
                 if ((long long)blocks * kUWarps > nitems) blocks = (int)((nitems + kUWarps - 1) / kUWarps);
                 if (upd3m) LAUNCH(KC_CHOL_UPDATE, st, k_chol_update<true><<<blocks, kUWarps * 32, kUpdSmem, st>>>(a, J, ipf));
@@ -1834,6 +1846,7 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         SolveArgs S;
         S.X = A.X; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
         S.nf = A.nf; S.Mxmax = l.Mxmax; S.dc = 1; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
+        S.counter = (int32_t*)(base + l.off_cnt);
         static const bool use_toeplitz = !(getenv("EAQHM_NO_TOEPLITZ") && atoi(getenv("EAQHM_NO_TOEPLITZ")));
         const bool toeplitz = adapt == 0 && use_toeplitz;
         if (A.a0_real) {
@@ -1880,8 +1893,8 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
         CUDA_TRY(cudaMalloc(&d_R, (size_t)(P + 1) * Pp * 16));
         CUDA_TRY(cudaMemset(d_R, 0, (size_t)(P + 1) * Pp * 16));
         CUDA_TRY(cudaMalloc(&d_x, (size_t)P * 16));
-        CUDA_TRY(cudaMalloc(&d_meta, 4 * sizeof(int32_t)));
-        const int32_t meta[4] = {M, L, 0, 0};
+        CUDA_TRY(cudaMalloc(&d_meta, 8 * sizeof(int32_t)));
+        const int32_t meta[8] = {M, L, 0, 0, 0, 0, 0, 0};      // [0] columns, [1] samples, [2..3] status, [4] work counter
         CUDA_TRY(cudaMemcpy(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice));
         double2* Rb = d_R + (size_t)P * Pp;
         if (f0range) {
@@ -1898,6 +1911,7 @@ static int seam_solve(const double* s, int L, int M, const double* win, double f
         SolveArgs S;
         S.X = d_X; S.R = d_R; S.x = d_x; S.Mcols = d_meta; S.Lrows = d_meta + 1;
         S.nf = 1; S.Mxmax = M; S.dc = 0; S.Pmax = P; S.Pp = Pp; S.Lp = Lp; S.status = d_meta + 2;
+        S.counter = d_meta + 4;
         int r2 = eaqhm_launch_gram_solve(S, 0, true);
         if (r2 != EAQHM_OK) return r2;
         CUDA_TRY(cudaDeviceSynchronize());

@@ -155,13 +155,20 @@ def _parallel_fill(pairs):
     list(_COPY_POOL.map(lambda p: np.copyto(p[0], p[1]), pairs))
 
 
+def _pinned(tag, n, dtype):
+    """Cached pinned staging buffer (grow-only, one per tag; page-locking gigabytes takes seconds, so long signals
+    call this before their loop starts)."""
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < n or buf.dtype != dtype:
+        buf = torch.empty(n, dtype=dtype, pin_memory=True)
+        _PINNED[tag] = buf
+    return buf
+
+
 def _to_host(t, tag):
     """Device tensor -> numpy through a cached pinned staging buffer (grow-only, one per tag)."""
     n = t.numel()
-    buf = _PINNED.get(tag)
-    if buf is None or buf.numel() < n or buf.dtype != t.dtype:
-        buf = torch.empty(n, dtype=t.dtype, pin_memory=True)
-        _PINNED[tag] = buf
+    buf = _pinned(tag, n, t.dtype)
     view = buf[:n]
     view.copy_(t.reshape(-1), non_blocking=True)
     return view
@@ -458,8 +465,15 @@ class Engine:
         check_not_pd(int(self.status[0].item()))
         return SRER, best_a, frames_solved
 
+    def prepare_readback(self):
+        """Page-lock the staging buffers of results() ahead of the loop."""
+        _pinned("s", self.s_best.numel(), torch.float64)
+        for i, x in enumerate(self.best):
+            _pinned("k%d" % i, x.numel(), torch.float64)
+
     def run(self, on_adaptation=None):
         """Adaptation loop + copy of the results to host arrays.  Returns one Result per utterance."""
+        self.prepare_readback()
         return self.results(*self.run_device(on_adaptation, prefetch_results=True))
 
     def results(self, SRER, best_a, frames_solved=0):

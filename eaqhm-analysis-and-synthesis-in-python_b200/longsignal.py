@@ -25,8 +25,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import (BufferPool, Engine, Result, Utterance, _parallel_copies, _parallel_fill, _to_host, check_not_pd,
-                     merge_stats)
+from .engine import (BufferPool, Engine, Result, Utterance, _parallel_copies, _parallel_fill, _pinned, _to_host,
+                     check_not_pd, merge_stats)
 from .host import FrameTables
 from .sharding import SPLINE_HALO_KNOTS, contiguous_blocks
 
@@ -368,7 +368,16 @@ class LongSignalEngine:
                                  fallback_flags=int(status[1]), exchanged_bytes=int(self.exchanged_bytes),
                                  owned_samples=(self.R_lo, self.R_hi), owned_frames=(self.F_lo, self.F_hi)))
 
+    def prepare_readback(self):
+        """Page-lock the staging buffers of results() ahead of the loop (seconds for an hour of signal)."""
+        n = self.F_hi - self.F_lo
+        _pinned("ls", self.s_best.numel(), torch.float64)
+        for i in range(3):
+            _pinned("lk%d" % i, n * self.Kmax, torch.float64)
+        _pinned("lk3", n, torch.float64)
+
     def run(self, on_adaptation=None, fixed_adaptations=None):
+        self.prepare_readback()
         return self.results(*self.run_device(on_adaptation, fixed_adaptations, prefetch_results=True))
 
 
