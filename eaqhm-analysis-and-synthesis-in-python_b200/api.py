@@ -134,7 +134,7 @@ def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', s
                               maxAdpt: int = 10, pitchPeriods: int = 3, analysisWindow: int = 32,
                               fullWaveform: bool = True, fc: int = 0, partials: int = 0,
                               printPrompts: bool = True, loadingScreen: bool = True, *, f0s=None, frames=None,
-                              return_tensors: bool = False):
+                              return_tensors: bool = False, host_preprocessing: bool = False):
     """Same call signature and return values as the reference (functions.py:35-81,418).
 
     Keyword-only extensions: ``f0s`` ((n,3) [t,f0,strength] track, replaces SWIPE') and ``frames``
@@ -144,7 +144,9 @@ def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', s
     ``return_tensors=True`` returns the per-frame parameters as the dense ``engine.Result`` (a0 (No_ti,), am / fm / ph
     (No_ti, Kmax), flags) in place of the list of ``Deterministic`` objects, whose construction costs more than the
     whole GPU path for one utterance (``pack_det_components(result)`` converts later; ``params.save_result`` /
-    ``params.resynthesize`` work on the tensor form).
+    ``params.resynthesize`` work on the tensor form); SWIPE' and the energy loop of the speech / voiced flags run on the
+    GPU (preprocess.swipep_gpu, voicedUnvoicedFrames_gpu) unless ``host_preprocessing=True`` selects their numpy
+    restatements (same pitch track and flags).
     """
     from . import preprocess
     startTime = time()
@@ -154,12 +156,14 @@ def eaQHMAnalysisAndSynthesis(speechFile: str, gender: str or tuple = 'other', s
     f0min, f0max = host.gender_limits(gender)
     grid = np.arange(0, len(s) - 1, round(fs * 5 / 1000)) / fs                # functions.py:113
     if f0s is None:
-        f0s = preprocess.swipep(s, fs, [f0min, f0max])                        # functions.py:111
+        swipe = preprocess.swipep if host_preprocessing else preprocess.swipep_gpu
+        f0s = swipe(s, fs, [f0min, f0max])                                    # functions.py:111
     f0s = np.asarray(f0s, float)
     if not (len(f0s) == len(grid) and np.array_equal(f0s[:, 0], grid)):       # already on the 5 ms grid?
         f0s = preprocess.getLinear(f0s, grid)
     if frames is None:
-        speech5, voiced5, frame_step = preprocess.voicedUnvoicedFrames(s, fs, gender)   # functions.py:125
+        vuv = preprocess.voicedUnvoicedFrames if host_preprocessing else preprocess.voicedUnvoicedFrames_gpu
+        speech5, voiced5, frame_step = vuv(s, fs, gender)                     # functions.py:125
     else:
         speech5, voiced5, frame_step = frames
 

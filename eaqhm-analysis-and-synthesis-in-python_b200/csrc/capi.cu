@@ -79,7 +79,7 @@ int eaqhm_sm_count() {
 
 static const char* kKernelNames[KC_COUNT] = {"fallback_flags", "active", "basis", "gram", "chol_solve", "accept",
                                              "run_moments", "a0_moments", "interp", "synth", "reduce", "var_pass",
-                                             "snapshot", "chol_update"};
+                                             "snapshot", "chol_update", "swipe"};
 
 extern "C" int eaqhm_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -38,7 +38,7 @@ void eaqhm_set_error(const char* fmt, ...);
 // ---- launch accounting / per-kernel-class CUDA-event timing (capi.cu) -----------------------
 enum KernelClass {
     KC_FALLBACK = 0, KC_ACTIVE, KC_BASIS, KC_GRAM, KC_CHOL, KC_ACCEPT, KC_RUN_MOMENTS, KC_A0_MOMENTS,
-    KC_INTERP, KC_SYNTH, KC_REDUCE, KC_VARPASS, KC_SNAPSHOT, KC_CHOL_UPDATE, KC_COUNT
+    KC_INTERP, KC_SYNTH, KC_REDUCE, KC_VARPASS, KC_SNAPSHOT, KC_CHOL_UPDATE, KC_SWIPE, KC_COUNT
 };
 void eaqhm_prof_begin(int kc, cudaStream_t st);
 void eaqhm_prof_end(int kc, cudaStream_t st);

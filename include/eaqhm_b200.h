@@ -188,6 +188,39 @@ int eaqhm_eaqhmLS_complexamps(const double* s, int32_t L, const double* am, cons
 int eaqhm_phase_integr_interpolation(const double* fm_recon, const double* ph_recon, int64_t length,
                                      const int64_t* indices, int32_t n, double* out);
 
+/* functions.py:616-634 (voicedUnvoicedFrames): energy_db[i] = 20 log10 numpy.std(s[ti + (-mid-1 .. mid-1)]) for the 5 ms
+ * frame centres ti = 1 + i*step, window_len = 2*mid + 1 samples (30 ms, odd), likewise for the low-passed signal; NaN
+ * for frames whose window leaves the signal.  DEVICE buffers; thresholds and the median filter stay with the caller. */
+int eaqhm_vuv_energy(const double* s, const double* s_smooth, int64_t length, int32_t window_len, int32_t step,
+                     int64_t nframes, double* energy_db, double* energy_smooth_db, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * SWIPE' pitch-strength matrix (host preprocessing of the path: functions.py:111 -> SWIPE.py:14-132), DEVICE buffers.
+ * The caller (eaqhm_b200/preprocess.py:swipep_gpu) owns the grids that depend on the sample rate and pitch range only
+ * and does the parabolic refinement of the winning candidate (SWIPE.py:106-131) on the host.
+ * ------------------------------------------------------------------------- */
+
+/* SWIPE.py:56-72,140-142 for one power-of-two window size ws (<= 8192): frame `seg` covers the zero-padded samples
+ * [seg*hop - pad_front, +ws); Hann `window`[ws] with sumw2 = sum(window^2); PSD on the rfft frequencies f[ws/2+1];
+ * linear interpolation onto ferb[nerb] (lo[e] = index of the rfft bin at or below ferb[e], <= ws/2 - 1), square root,
+ * unit norm per frame.  Ln: [nerb][nseg]. */
+int eaqhm_swipe_loudness(const double* x, int64_t n_x, int32_t ws, int32_t hop, int32_t pad_front,
+                         const double* window, double fs, double sumw2, const double* f, const int32_t* lo,
+                         const double* ferb, int32_t nerb, int64_t nseg, double* Ln, void* stream);
+
+/* SWIPE.py:146: Si[ncand][nseg] = K[ncand][nerb] x Ln[nerb][nseg] (K = candidate kernels, SWIPE.py:166-184). */
+int eaqhm_swipe_strength(const double* K, int32_t ncand, int32_t nerb, const double* Ln, int64_t nseg, double* Si,
+                         void* stream);
+
+/* SWIPE.py:92-104: S[rows[r]][t] += mu[r] * (linear interpolation of Si[r] at output time t): hi[t] = upper frame index
+ * (< 0: t outside the frame times -> NaN), w1[t] = t - tim[hi-1], w2[t] = tim[hi] - tim[hi-1].  S: [npc][nt]. */
+int eaqhm_swipe_accumulate(const double* Si, int32_t ncand, int64_t nseg, const int32_t* rows, const double* mu,
+                           const int32_t* hi, const double* w1, const double* w2, int64_t nt, double* S, void* stream);
+
+/* SWIPE.py:108: best[t] = numpy.argmax(S[:, t]) (first NaN, else first maximum); y[3][nt] = S[best-1], S[best],
+ * S[best+1] at t (NaN beyond the candidate range). */
+int eaqhm_swipe_argmax(const double* S, int32_t npc, int64_t nt, int32_t* best, double* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

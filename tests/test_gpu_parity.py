@@ -566,3 +566,48 @@ def test_api_returns_tensors_on_request(tmp_path):
                                                       return_tensors=True)
     assert isinstance(res, engine.Result) and res.am.shape == (len(res.ti), int(g["Kmax"]))
     assert np.abs(s_recon - g["s_recon"]).max() <= TOL_S and np.abs(np.array(SRER) - g["SRER"]).max() <= TOL_SRER
+
+
+# ---------------------------------------------------------------------------------------------
+# preprocessing stages on the GPU: same pitch track and flags as the reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,plim", [("sa19", (160, 300)), ("synth_child_vo", (250, 500)), ("synth_low", (70, 180))])
+def test_swipe_on_the_gpu_gives_the_cpu_pitch_track(name, plim):
+    """csrc/preproc.cu (hand-written FFT -> ERB loudness -> kernel products -> interpolation -> argmax) against the numpy
+    restatement of SWIPE.py:14-132, which tests/test_preprocess_cpu.py pins to the reference: identical pitch in every 1 ms
+    frame (the refinement snaps it to a 1/768-octave grid), strengths to rounding."""
+    from eaqhm_b200 import preprocess
+    g, _ = load_golden(name)
+    s = g["pcm"].astype(float) / 32768
+    fs = int(g["fs"])
+    cpu = preprocess.swipep(s, fs, list(plim))
+    gpu = preprocess.swipep_gpu(s, fs, list(plim))
+    assert cpu.shape == gpu.shape and (cpu[:, 0] == gpu[:, 0]).all()
+    assert ((cpu[:, 1] == gpu[:, 1]) | (np.isnan(cpu[:, 1]) & np.isnan(gpu[:, 1]))).all()
+    both = np.isfinite(cpu[:, 2]) & np.isfinite(gpu[:, 2])
+    assert (np.isfinite(cpu[:, 2]) == np.isfinite(gpu[:, 2])).all() and np.abs(cpu[both, 2] - gpu[both, 2]).max() <= 1e-12
+
+
+def test_sa19_pitch_from_the_gpu_is_the_reference_track():
+    """The 5 ms f0 grid the hot path consumes (functions.py:111-113), from the GPU SWIPE', equals the one captured from the
+    unmodified reference run (fixture sa19.npz)."""
+    from eaqhm_b200 import preprocess
+    g, _ = load_golden("sa19")
+    s = g["pcm"].astype(float) / 32768
+    grid = np.arange(0, len(s) - 1, 80) / 16000
+    f0s = preprocess.getLinear(preprocess.swipep_gpu(s, 16000, [160, 300]), grid)
+    assert f0s.shape == g["f0s"].shape and np.abs(f0s[:, 1] - g["f0s"][:, 1]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name,gender", [("sa19", "female"), ("synth_child_vo", (250, 500)), ("synth_silence", (90, 250))])
+def test_speech_voiced_flags_on_the_gpu_equal_the_reference(name, gender):
+    """k_vuv_energy + thresholds + 4-tap median (functions.py:577-642, misc.py:184-206) against the flags the unmodified
+    reference estimated for the fixture."""
+    from eaqhm_b200 import preprocess
+    g, _ = load_golden(name)
+    s = g["pcm"].astype(float) / 32768
+    speech, voiced, fstep = preprocess.voicedUnvoicedFrames_gpu(s, int(g["fs"]), gender)
+    assert fstep == int(g["frame_step"])
+    assert (np.asarray(speech, bool) == g["speech5"]).all() and (np.asarray(voiced, bool) == g["voiced5"]).all()
+    sc, vc, _ = preprocess.voicedUnvoicedFrames(s, int(g["fs"]), gender)
+    assert (speech == sc).all() and (voiced == vc).all()
