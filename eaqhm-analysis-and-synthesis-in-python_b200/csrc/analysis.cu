@@ -36,6 +36,8 @@ struct AnaArgs {
     double2* x;                     // [chunk][Pmax]
     int32_t* status;
     double* flop_stats;             // [3] += algorithmic flops of the Gram / Cholesky / basis+rhs (may be null)
+    uint8_t* slow;                  // [chunk][nnz_max] columns the fast basis kernel left to k_basis<true> (gaps, run ends, fallback)
+    int32_t slow_only;              // k_basis<true> builds only the columns flagged in `slow`
     int32_t a0_real;                // adaptation 0 solved as two real systems (k_a0_build_real, k_chol_real)
     int32_t store_X;                // k_basis<false> writes the basis planes (only the dense-Gram path reads them)
 };
@@ -165,6 +167,15 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int jl = blockIdx.x;
+    if (ADAPT && A.slow_only) {     // nothing left to this kernel in most frames: leave before touching shared memory
+        __shared__ int any_slow;
+        if (tid == 0) any_slow = 0;
+        __syncthreads();
+        const int nzq = A.Mcols[jl] / 2;
+        for (int it = tid; it < nzq; it += kBasisThreads) if (A.slow[(size_t)jl * A.nnz_max + it]) any_slow = 1;
+        __syncthreads();
+        if (!any_slow) return;
+    }
     const int g = A.t.alist[A.j0 + jl];
     const int N = A.t.N[g], L = 2 * N + 1;
     const int Mx = A.Mcols[jl], nz = Mx / 2, P = 2 * Mx + 2;
@@ -204,6 +215,7 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
     const double f0 = A.t.f0[g];
 
     for (int it = warp; it <= nz && warp < A.nwb; it += A.nwb) {
+        if (ADAPT && A.slow_only && (it == nz || !A.slow[(size_t)jl * A.nnz_max + it])) continue;   // built by k_basis_fast
         if (it == nz) {   // DC column: E2 = 1 (fm = 0, am = 0 -> (eps+0)/(0+eps) = 1), X = w
             double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
             for (int n = lane; n < L; n += 32) {
@@ -456,6 +468,154 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
             cn.store(nz + it, Mx, Rb, Rd0, Rd1);
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Adaptive basis, fast path only.  Inside one run of a harmonic the basis phasor is a ratio of two phasor-track values
+// (see k_basis<true>), so a column needs no gap scan, no running sum and no per-warp column buffers: this kernel builds
+// every such column with shared memory for the window alone (four resident CTAs per SM instead of two) and two passes
+// over the samples, the second one re-reading the (L1-resident) track values for the mirrored column instead of parking
+// them in shared memory.  A column that turns out not to be clean (a zero sample, the 140 Hz fallback, a wrapped
+// window) is flagged in A.slow and rebuilt, together with its sums, by k_basis<true> in slow-only mode.  Same
+// arithmetic, operation for operation, as the fast path of k_basis<true>.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBasisThreads, 3) k_basis_fast(AnaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jl = blockIdx.x;
+    const int g = A.t.alist[A.j0 + jl];
+    const int N = A.t.N[g], L = 2 * N + 1;
+    const int Mx = A.Mcols[jl], nz = Mx / 2, P = 2 * Mx + 2;
+    const int u = A.t.utt[g];
+    const int64_t us = A.t.ustart[u], ul = A.t.ulen[u];
+    const int64_t cl = A.t.pos[g] - us;
+    const double fs = A.t.fs;
+    double* w = reinterpret_cast<double*>(smem_raw);
+    double* ws = w + A.Lp;
+    for (int n = tid; n < L; n += kBasisThreads) {
+        const double nn = (double)(1 - L + 2 * n), den = (double)(L - 1);
+        const double wn = 0.54 + 0.46 * cos((kPi * nn) / den);                 // numpy.hamming (functions.py:200)
+        int64_t il = cl - N + n;
+        if (il < 0) il += ul;
+        w[n] = wn;
+        ws[n] = wn * A.s[us + il];
+    }
+    __syncthreads();
+    double* Xr = A.X + (size_t)jl * 2 * A.Mxmax * A.Lp;
+    double* Xi = Xr + (size_t)A.Mxmax * A.Lp;
+    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
+    double2* Rb = RF + (size_t)P * A.Pp;
+    double2* Rd0 = RF + (size_t)(2 * Mx) * A.Pp;
+    double2* Rd1 = RF + (size_t)(2 * Mx + 1) * A.Pp;
+    const int16_t* act = A.act + (int64_t)jl * A.nnz_max;
+    uint8_t* slow = A.slow + (size_t)jl * A.nnz_max;
+    const bool frame_ok = cl - N >= 0;                                         // no wrapped indices
+
+    for (int it = warp; it <= nz; it += kBasisWarps) {
+        if (it == nz) {   // DC column: X = w
+            double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            for (int n = lane; n < L; n += 32) {
+                const double wn = w[n], nc = (double)(n - N), v = ws[n];
+                s0 += wn * v;        s1 += nc * wn * v;
+                q0 += wn * wn;       q1 += nc * wn * wn;      q2 += nc * nc * wn * wn;
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1); q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2);
+            if (lane == 0) {
+                Rb[2 * Mx] = make_double2(s0, 0.0);       Rb[2 * Mx + 1] = make_double2(s1, 0.0);
+                Rd0[2 * Mx] = make_double2(q0, 0.0);
+                Rd1[2 * Mx] = make_double2(q1, 0.0);      Rd1[2 * Mx + 1] = make_double2(q2, 0.0);
+            }
+            continue;
+        }
+        const int k = act[it];
+        if (!frame_ok) { if (lane == 0) slow[it] = 1; continue; }
+        const int64_t off = (int64_t)k * A.t.T + us + (cl - N);
+        const double* __restrict__ fmk = A.fm_cur + off;
+        const double* __restrict__ amk = A.am_cur + off;
+        const double* __restrict__ zck = A.zc_cur + off;
+        const double* __restrict__ zsk = A.zs_cur + off;
+        double* __restrict__ pr = Xr + (size_t)it * A.Lp;
+        double* __restrict__ pi = Xi + (size_t)it * A.Lp;
+        double* __restrict__ nr = Xr + (size_t)(nz + it) * A.Lp;
+        double* __restrict__ ni = Xi + (size_t)(nz + it) * A.Lp;
+        const double fmid = fmk[N], ainv = 1.0 / (amk[N] + kAmEps);
+        const double zcc = zck[N], zsc = zsk[N];
+        // pass 1: +f column, its sums, the zero test and S[N-1] = sum of fm over the first N samples
+        bool clean = true;
+        double s_lo = 0.0;
+        ColSums cs_;
+        cs_.zero();
+        for (int n0 = lane; n0 < L; n0 += 128) {
+            double fq[4], aq[4], cq[4], sq[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int n = n0 + 32 * q, ns = n < L ? n : 0;
+                fq[q] = fmk[ns]; aq[q] = amk[ns]; cq[q] = zck[ns]; sq[q] = zsk[ns];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int n = n0 + 32 * q;
+                if (n >= L) break;
+                if (k == 0) {                                                   // in-place fallback of a frame centred here (Q6)
+                    const int64_t il = cl - N + n;
+                    if ((il % A.t.step) == 0) {
+                        const int64_t gi = A.t.gfirst[u] + il / A.t.step;
+                        if (gi <= g && gi < A.t.gfirst[u] + A.t.gcount[u] && A.fb[gi]) clean = false;
+                    }
+                }
+                clean &= (fq[q] != 0.0);
+                if (n < N) s_lo += fq[q];
+                const double nc = (double)(n - N), wn = w[n], v = ws[n];
+                const double c1 = cq[q], s1 = sq[q];
+                const double cs = c1 * zcc + s1 * zsc, sn = s1 * zcc - c1 * zsc;
+                const double r = (kAmEps + aq[q]) * ainv;
+                const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+                pr[n] = xr; pi[n] = xi;
+                cs_.add(xr, xi, nc, wn, v);
+            }
+        }
+        clean = __all_sync(0xffffffffu, clean);
+        if (!clean) { if (lane == 0) slow[it] = 1; continue; }
+        s_lo = warp_sum(s_lo);
+        s_lo = __shfl_sync(0xffffffffu, s_lo, 0);
+        cs_.reduce();
+        if (lane == 0) cs_.store(it, Mx, Rb, Rd0, Rd1);
+        // pass 2: time-reversed -f column (Q2): E1neg[n] = E1[L-2-n] rho, rho = exp(j 2 pi fm[N] / fs), amplitude ratio of
+        // sample L-1-n; the index pairs (n, L-2-n) share their four track loads
+        cs_.zero();
+        double rs, rc;
+        sincos((kTwoPi * fmid) / fs, &rs, &rc);
+        for (int n = lane; n < N; n += 32) {
+            const int n2 = L - 2 - n;
+            const double c1 = zck[n], s1 = zsk[n], c2 = zck[n2], s2 = zsk[n2];
+            const double cs1 = c1 * zcc + s1 * zsc, sn1 = s1 * zcc - c1 * zsc;   // E1[n]
+            const double cs2 = c2 * zcc + s2 * zsc, sn2 = s2 * zcc - c2 * zsc;   // E1[n2]
+            {
+                const double er = cs2 * rc - sn2 * rs, ei = cs2 * rs + sn2 * rc;
+                const double r = (kAmEps + amk[L - 1 - n]) * ainv, wn = w[n];
+                const double xr = (r * er) * wn, xi = (r * ei) * wn;
+                nr[n] = xr; ni[n] = xi;
+                cs_.add(xr, xi, (double)(n - N), wn, ws[n]);
+            }
+            {
+                const double er = cs1 * rc - sn1 * rs, ei = cs1 * rs + sn1 * rc;
+                const double r = (kAmEps + amk[n + 1]) * ainv, wn = w[n2];
+                const double xr = (r * er) * wn, xi = (r * ei) * wn;
+                nr[n2] = xr; ni[n2] = xi;
+                cs_.add(xr, xi, (double)(n2 - N), wn, ws[n2]);
+            }
+        }
+        if (lane == 0) {
+            double sn, cs;
+            sincos((kTwoPi * (0.0 - s_lo)) / fs, &sn, &cs);
+            const double r = (kAmEps + amk[0]) * ainv, wn = w[L - 1];
+            const double xr = (r * cs) * wn, xi = (r * sn) * wn;
+            nr[L - 1] = xr; ni[L - 1] = xi;
+            cs_.add(xr, xi, (double)N, wn, ws[L - 1]);
+        }
+        cs_.reduce();
+        if (lane == 0) cs_.store(nz + it, Mx, Rb, Rd0, Rd1);
     }
 }
 
@@ -1118,10 +1278,10 @@ __device__ unsigned long long g_chol_cycles[8];
 #endif
 constexpr bool kChol3M = EAQHM_CHOL_3M != 0;
 
-template <int kNW>
 #ifndef EAQHM_CHOL_THREADS_PER_SM
 #define EAQHM_CHOL_THREADS_PER_SM 512
 #endif
+template <int kNW>
 __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 32)) k_chol_solve(SolveArgs A, int panel) {
     // panel < 0: the whole factorisation and the back substitution in one launch.  panel = J >= 0: only the block columns
     // of column panel J (kPanelW columns), whose tiles k_chol_update has already updated with every earlier panel, so the
@@ -1134,11 +1294,11 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
     const int Pp = A.Pp;
     __shared__ double2 D[kNb][kNb + 1];               // factored diagonal block of the current block column
     __shared__ double2 Tall[kNW][kNb][kNb + 1];       // per-warp staging tile
+    double2 (*T)[kNb + 1] = Tall[warp];
     __shared__ double2 red[kThreads / 16][17];
     __shared__ double Dorig[kNW][kNb];                // diagonal of R before the update: scale of the pivot test
     __shared__ int bad;
     extern __shared__ __align__(16) double2 xs[];     // [Pmax] solution
-    double2 (*T)[kNb + 1] = Tall[warp];
     if (tid == 0) bad = 0;
     __syncthreads();
 #ifdef EAQHM_CHOL_TIMING
@@ -1317,6 +1477,7 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
         TMARK(5);           // wait end of block column
     }
 
+    if (tid == 0 && bad && A.status) { atomicAdd(&A.status[0], 1); bad = 0; }
     if (jbk_hi < ncb) return;                         // more panels to come
     // back substitution: row P of the factor is y^H, so y_q = conj(R[P][q]); solve L^H x = y.
     // Per block column (last to first): the diagonal block is brought into shared memory with one coalesced load
@@ -1374,7 +1535,6 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
 #endif
     double2* xo = A.x + (size_t)jl * A.Pmax;
     for (int p = tid; p < P; p += kThreads) xo[p] = xs[p];
-    if (tid == 0 && bad && A.status) atomicAdd(&A.status[0], 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1700,6 +1860,7 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
     l.off_fb = o;  o = align_up(o + G, 256);
     l.off_M = o;   o = align_up(o + (int64_t)chunk * 4 * 2, 256);
     l.off_act = o; o = align_up(o + (int64_t)chunk * nnz_max * 2, 256);
+    l.off_slow = o; o = align_up(o + (int64_t)chunk * nnz_max, 256);
     l.off_X = o;   o = align_up(o + (int64_t)chunk * 2 * l.Mxmax * l.Lp * 8, 256);
     l.off_R = o;   o = align_up(o + (int64_t)chunk * (l.Pmax + 1) * l.Pp * 16, 256);
     l.off_x = o;   o = align_up(o + (int64_t)chunk * l.Pmax * 16, 256);
@@ -1805,6 +1966,8 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     A.Mcols = (int32_t*)(base + l.off_M);
     A.Lrows = A.Mcols + chunk;
     A.act = (int16_t*)(base + l.off_act);
+    A.slow = base + l.off_slow;
+    A.slow_only = 0;
     A.X = (double*)(base + l.off_X);
     A.R = (double2*)(base + l.off_R);
     A.x = (double2*)(base + l.off_x);
@@ -1823,6 +1986,7 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         CHECK_ARG(dev >= 0);
         CUDA_TRY(cudaFuncSetAttribute(k_basis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(k_basis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_basis_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     }
     CHECK_ARG(smem <= 200 * 1024);
 
@@ -1841,8 +2005,21 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         A.j0 = j0;
         A.nf = min(chunk, tab->nA - j0);
         LAUNCH(KC_ACTIVE, st, k_active<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
-        if (adapt == 0) LAUNCH(KC_BASIS, st, k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A));
-        else LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
+        // adaptive basis: fast-path kernel for the columns inside one run (phasor tracks present), k_basis<true> for the rest
+        static const bool two_kernels = !(getenv("EAQHM_BASIS_FAST") && atoi(getenv("EAQHM_BASIS_FAST")) == 0);
+        const size_t fsm = (size_t)l.Lp * 16;
+        const bool fast = adapt > 0 && two_kernels && A.zc_cur != nullptr && A.zs_cur != nullptr && fsm <= 64 * 1024;
+        if (adapt == 0) {
+            LAUNCH(KC_BASIS, st, k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A));
+        } else if (fast) {
+            CUDA_TRY(cudaMemsetAsync(A.slow, 0, (size_t)A.nf * l.nnz_max, st));
+            LAUNCH(KC_BASIS, st, k_basis_fast<<<A.nf, kBasisThreads, fsm, st>>>(A));
+            A.slow_only = 1;
+            LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
+            A.slow_only = 0;
+        } else {
+            LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
+        }
         SolveArgs S;
         S.X = A.X; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
         S.nf = A.nf; S.Mxmax = l.Mxmax; S.dc = 1; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;

@@ -99,7 +99,7 @@ __device__ __forceinline__ double warp_max(double v) {
 // ---- analysis stage internals (analysis.cu) -------------------------------------------
 struct AnaLayout {
     int32_t nnz_max, Mxmax, Pmax, Pp, Lp;  // Mxmax = 2*nnz_max generic columns, Pmax = 2*Mxmax+2, Pp = row pitch of R, Lp = pitch of X rows
-    int64_t off_fb, off_M, off_act, off_X, off_R, off_x, off_cnt, total;
+    int64_t off_fb, off_M, off_act, off_slow, off_X, off_R, off_x, off_cnt, total;
 };
 AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max);
 
