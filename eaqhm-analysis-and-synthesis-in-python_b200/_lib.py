@@ -96,6 +96,8 @@ _SIGNATURES = {
     "eaqhm_eaqhmLS_complexamps": (C.c_int, [c_f64p, C.c_int32, c_f64p, c_f64p, C.c_int32, c_f64p, C.c_double,
                                             c_f64p, c_f64p]),
     "eaqhm_phase_integr_interpolation": (C.c_int, [c_f64p, c_f64p, C.c_int64, c_i64p, C.c_int32, c_f64p]),
+    "eaqhm_filtfilt_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eaqhm_vuv_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "eaqhm_swipe_loudness": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_double,

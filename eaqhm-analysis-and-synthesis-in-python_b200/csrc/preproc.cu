@@ -177,6 +177,61 @@ __global__ void __launch_bounds__(128) k_vuv_energy(const double* __restrict__ s
     }
 }
 
+// scipy.signal.filtfilt(b, a, x) (default 'pad' method: odd extension by padlen samples, steady-state initial conditions
+// lfilter_zi scaled by the first sample, forward pass, backward pass) as the reference uses it for its elliptic filters
+// (misc.py:167-182 via functions.py:90-91,579,582), for a BATCH of signals: one thread per signal runs the two recursions
+// sequentially in time, in scipy's direct-form-II-transposed operation order and without fused multiply-adds, so the
+// output equals scipy's bit for bit.  A corpus filters thousands of utterances per launch; a single long signal is better
+// served by the host (the recursion is sequential).
+template <int NT>   // taps of b and a (filter order + 1)
+__global__ void __launch_bounds__(64) k_filtfilt_batch(const double* __restrict__ x, const int64_t* __restrict__ start,
+                                                       const int64_t* __restrict__ len, int nutt, const double* __restrict__ bc,
+                                                       const double* __restrict__ ac, const double* __restrict__ zic,
+                                                       int padlen, double* __restrict__ y, double* __restrict__ work,
+                                                       const int64_t* __restrict__ wstart) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nutt) return;
+    double b[NT], a[NT], z[NT - 1];
+#pragma unroll
+    for (int i = 0; i < NT; i++) { b[i] = bc[i]; a[i] = ac[i]; }
+    const double* xs = x + start[u];
+    double* ys = y + start[u];
+    double* w = work + wstart[u];
+    const int64_t L = len[u], E = L + 2 * (int64_t)padlen;
+    const double xl = __dmul_rn(2.0, xs[0]), xr = __dmul_rn(2.0, xs[L - 1]);
+    // one sample of scipy's _linear_filter (direct form II transposed), its operation order, no contraction
+#define EAQHM_FILT_STEP(xn, yn)                                                                            \
+    {                                                                                                      \
+        yn = __dadd_rn(z[0], __dmul_rn(b[0], xn));                                                         \
+        _Pragma("unroll") for (int i = 0; i < NT - 2; i++)                                                 \
+            z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, b[i + 1])), __dmul_rn(yn, a[i + 1]));       \
+        z[NT - 2] = __dsub_rn(__dmul_rn(xn, b[NT - 1]), __dmul_rn(yn, a[NT - 1]));                         \
+    }
+    // forward pass over the odd extension (scipy.signal._arraytools.odd_ext) of the signal
+    const double x0 = __dsub_rn(xl, xs[padlen]);
+#pragma unroll
+    for (int i = 0; i < NT - 1; i++) z[i] = __dmul_rn(zic[i], x0);
+    for (int64_t i = 0; i < E; i++) {
+        double xn, yn;
+        if (i < padlen) xn = __dsub_rn(xl, xs[padlen - i]);
+        else if (i < padlen + L) xn = xs[i - padlen];
+        else xn = __dsub_rn(xr, xs[L - 2 - (i - padlen - L)]);
+        EAQHM_FILT_STEP(xn, yn);
+        w[i] = yn;
+    }
+    // backward pass; keep the samples of the signal proper
+    const double y0 = w[E - 1];
+#pragma unroll
+    for (int i = 0; i < NT - 1; i++) z[i] = __dmul_rn(zic[i], y0);
+    for (int64_t i = E - 1; i >= padlen; i--) {
+        const double xn = w[i];
+        double yn;
+        EAQHM_FILT_STEP(xn, yn);
+        if (i < padlen + L) ys[i - padlen] = yn;
+    }
+#undef EAQHM_FILT_STEP
+}
+
 }  // namespace
 
 extern "C" int eaqhm_vuv_energy(const double* s, const double* s_smooth, int64_t length, int32_t window_len, int32_t step,
@@ -187,6 +242,17 @@ extern "C" int eaqhm_vuv_energy(const double* s, const double* s_smooth, int64_t
     const unsigned blocks = (unsigned)((nframes * 32 + 127) / 128);
     LAUNCH(KC_SWIPE, st, k_vuv_energy<<<blocks, 128, 0, st>>>(s, s_smooth, length, window_len, step, nframes, energy_db,
                                                               energy_smooth_db));
+    return EAQHM_OK;
+}
+
+extern "C" int eaqhm_filtfilt_batch(const double* x, const int64_t* start, const int64_t* len, int32_t nutt, const double* b,
+                                    const double* a, const double* zi, int32_t ntaps, int32_t padlen, double* y, double* work,
+                                    const int64_t* work_start, void* stream) {
+    CHECK_ARG(x && start && len && b && a && zi && y && work && work_start && nutt > 0);
+    CHECK_ARG(ntaps == 7 && padlen >= 1);        // the reference's filters are all 6th order (misc.py:178)
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH(KC_SWIPE, st, k_filtfilt_batch<7><<<(nutt + 63) / 64, 64, 0, st>>>(x, start, len, nutt, b, a, zi, padlen, y, work,
+                                                                            work_start));
     return EAQHM_OK;
 }
 

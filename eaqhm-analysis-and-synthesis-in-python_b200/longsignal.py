@@ -108,6 +108,21 @@ def allgather_rows(rows, world, dist):
     return torch.cat(parts, dim=0)
 
 
+def target_std(det, plan_all, rank, world, dist, device):
+    """numpy.std of the whole SRER target (functions.py:161) without any rank touching more than its own samples: (n,
+    mean, M2) of every shard's owned range, all-gathered once (fixed size, padded with n = 0 rows) and merged in shard
+    order with the pairwise-variance formula - the same arithmetic, hence the same bits, for any number of ranks."""
+    nmax = max(len(p) for p in plan_all)
+    st = np.zeros((nmax, 3))
+    for j, (own_lo, own_hi, _, _) in enumerate(plan_all[rank]):
+        x = det[own_lo:own_hi]
+        mu = x.mean()
+        st[j] = (own_hi - own_lo, mu, ((x - mu) ** 2).sum())
+    st = allgather_rows(torch.from_numpy(st).to(device), world, dist).cpu().numpy()
+    n_all, _, m2_all = merge_stats([("t", r[0], r[1], r[2]) for r in st if r[0] > 0])["t"]
+    return float(np.sqrt(m2_all / n_all))
+
+
 class LongSignalEngine:
     """eaQHM adaptation loop of one long signal on this rank's contiguous frame range (see the module docstring)."""
 
@@ -173,17 +188,7 @@ class LongSignalEngine:
         self.s_dev = torch.from_numpy(np.ascontiguousarray(s[self.X_lo:self.X_hi])).to(d)
         self.det_dev = self.s_dev if det_part is None else torch.from_numpy(
             np.ascontiguousarray(det[self.X_lo:self.X_hi])).to(d)
-        # functions.py:161: population standard deviation of the whole target, from (n, mean, M2) of every shard's owned
-        # samples merged in shard order (the same arithmetic whatever the number of ranks)
-        nmax = max(len(p) for p in self.plan_all)
-        st = np.zeros((nmax, 3))
-        for j, (own_lo, own_hi, _, _) in enumerate(self.plan):
-            x = det[own_lo:own_hi]
-            mu = x.mean()
-            st[j] = (own_hi - own_lo, mu, ((x - mu) ** 2).sum())
-        st = allgather_rows(torch.from_numpy(st).to(d), self.world, self.dist).cpu().numpy()
-        n_all, _, m2_all = merge_stats([("t", r[0], r[1], r[2]) for r in st if r[0] > 0])["t"]
-        self.std_det = float(np.sqrt(m2_all / n_all))
+        self.std_det = target_std(det, self.plan_all, self.rank, self.world, self.dist, d)        # functions.py:161
         f64 = dict(dtype=torch.float64, device=d)
 
         def store():

@@ -24,6 +24,44 @@ def ellipFilter(s, fs, fc, ftype="highpass"):
     return filtfilt(b, a, s)
 
 
+def ellipFilter_batch_gpu(signals, fs, fc, ftype="highpass", device="cuda"):
+    """ellipFilter for a batch of signals on the GPU (csrc/preproc.cu:k_filtfilt_batch: one thread per signal, scipy's
+    filtfilt recursion in scipy's operation order): a list of arrays with the same bits as [ellipFilter(s, fs, fc, ftype)
+    for s in signals].  Meant for corpora (thousands of utterances per launch); one signal is faster on the host."""
+    import ctypes as C
+    import torch
+    from scipy.signal import ellip, lfilter_zi
+    from . import _lib
+    L = _lib.lib()
+    if not torch.cuda.is_available():
+        raise _lib.EaqhmError("no CUDA device: ellipFilter_batch_gpu has no CPU fallback (use ellipFilter)")
+    dev = torch.device(device)
+    b, a = ellip(6, .5, 60, 2 * fc / fs, ftype)
+    if a[0] != 1.0:
+        b, a = b / a[0], a / a[0]
+    zi = lfilter_zi(b, a)
+    ntaps = max(len(a), len(b))
+    padlen = 3 * ntaps
+    lens = np.array([len(s) for s in signals], np.int64)
+    if np.any(lens <= padlen):
+        raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
+    start = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+    wstart = np.concatenate(([0], np.cumsum(lens + 2 * padlen)[:-1])).astype(np.int64)
+    with torch.cuda.device(dev):
+        up = lambda v, dt: torch.from_numpy(np.ascontiguousarray(v, dtype=dt)).to(dev)
+        x = up(np.concatenate([np.asarray(s, float).reshape(-1) for s in signals]), np.float64)
+        y = torch.empty_like(x)
+        work = torch.empty(int((lens + 2 * padlen).sum()), dtype=torch.float64, device=dev)
+        args = [up(start, np.int64), up(lens, np.int64), up(b, np.float64), up(a, np.float64), up(zi, np.float64),
+                up(wstart, np.int64)]
+        _lib.check(L.eaqhm_filtfilt_batch(x.data_ptr(), args[0].data_ptr(), args[1].data_ptr(), len(signals),
+                                          args[2].data_ptr(), args[3].data_ptr(), args[4].data_ptr(), ntaps, padlen,
+                                          y.data_ptr(), work.data_ptr(), args[5].data_ptr(),
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        out = y.cpu().numpy()
+    return [out[o:o + n].copy() for o, n in zip(start, lens)]
+
+
 def getLinear(v, t):
     """functions.py:644-680 for an array of times: rows [t, linear interpolation of v[:,1:] at t]; times before the
     first row take the first row, times at/after the last row the last one."""

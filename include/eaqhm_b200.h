@@ -168,8 +168,15 @@ int eaqhm_snapshot(const eaqhm_tables* tab, const uint8_t* improved, const eaqhm
                    const double* s_hat, double* s_best, const eaqhm_knots* best, void* stream);
 
 /* ---------------------------------------------------------------------------
- * Helper seams with HOST buffers (unit parity points; each call copies in, runs the
- * same device kernels as the stages above on one frame, copies out, synchronises).
+ * Helper seams with HOST buffers (unit parity points; each call copies in, runs device
+ * kernels on one frame, copies out, synchronises).  The two least-squares seams take
+ * explicit column tracks / frequencies like the reference's helpers, so they run the
+ * general route (explicit-column basis kernel, complex DMMA Gram k_gram_warp, complex
+ * Cholesky k_chol_solve): the SAME Gram and Cholesky kernels as stage A at adaptations
+ * >= 1.  Stage A's adaptation 0 uses a cheaper real even/odd formulation of the same
+ * normal equations (k_a0_build_real, k_chol_real) and its phase integration is fused into
+ * the interpolation kernel (k_interp_hw); those product kernels are covered end to end by
+ * the golden-fixture tests (tests/test_gpu_parity.py), the seams by their own.
  * ------------------------------------------------------------------------- */
 
 /* functions.py:420  iqhmLS_complexamps(s, f0range, window, fs) -> amplitudes, slopes.
@@ -187,6 +194,14 @@ int eaqhm_eaqhmLS_complexamps(const double* s, int32_t L, const double* am, cons
  * ascending knot samples; out has indices[n-1]-indices[0]+1 samples. */
 int eaqhm_phase_integr_interpolation(const double* fm_recon, const double* ph_recon, int64_t length,
                                      const int64_t* indices, int32_t n, double* out);
+
+/* misc.py:167-182 (ellipFilter -> scipy.signal.filtfilt(b, a, x), default odd padding of `padlen` samples and lfilter_zi
+ * initial conditions `zi`[ntaps-1]) for `nutt` signals packed in x: signal u is x[start[u] .. start[u]+len[u]), len[u] >
+ * padlen.  One thread per signal, scipy's operation order, no FMA: bit-identical output in y (same packing).  work: scratch,
+ * signal u uses work[work_start[u] .. +len[u]+2*padlen).  ntaps = len(b) = len(a) = 7 (6th order), a[0] = 1.  DEVICE buffers. */
+int eaqhm_filtfilt_batch(const double* x, const int64_t* start, const int64_t* len, int32_t nutt, const double* b,
+                         const double* a, const double* zi, int32_t ntaps, int32_t padlen, double* y, double* work,
+                         const int64_t* work_start, void* stream);
 
 /* functions.py:616-634 (voicedUnvoicedFrames): energy_db[i] = 20 log10 numpy.std(s[ti + (-mid-1 .. mid-1)]) for the 5 ms
  * frame centres ti = 1 + i*step, window_len = 2*mid + 1 samples (30 ms, odd), likewise for the low-passed signal; NaN

@@ -611,3 +611,18 @@ def test_speech_voiced_flags_on_the_gpu_equal_the_reference(name, gender):
     assert (np.asarray(speech, bool) == g["speech5"]).all() and (np.asarray(voiced, bool) == g["voiced5"]).all()
     sc, vc, _ = preprocess.voicedUnvoicedFrames(s, int(g["fs"]), gender)
     assert (speech == sc).all() and (voiced == vc).all()
+
+
+def test_batched_elliptic_filter_on_the_gpu_equals_scipy_bitwise():
+    """misc.py:167-182 (zero-phase 6th-order elliptic filter through scipy.signal.filtfilt) for a batch of
+    utterances in one launch, in scipy's operation order: the same bits as the host call, for the high-pass the reference
+    applies when fc > 0 (functions.py:90-91) and the two filters of its speech / voiced detector (functions.py:579,582)."""
+    from eaqhm_b200 import preprocess
+    rng = np.random.default_rng(4)
+    sigs = [rng.standard_normal(n) * 0.1 + 0.05 for n in (4000, 777, 16000, 48001)]
+    g, _ = load_golden("sa19")
+    sigs.append(g["pcm"].astype(float) / 32768)
+    for fs, fc, ftype in ((16000, 30, "highpass"), (16000, 1500, "lowpass"), (48000, 1000, "lowpass"), (16000, 70, "highpass")):
+        ys = preprocess.ellipFilter_batch_gpu(sigs, fs, fc, ftype)
+        for s, y in zip(sigs, ys):
+            assert (y == preprocess.ellipFilter(s, fs, fc, ftype)).all()

@@ -143,6 +143,14 @@ def _worker(rank, world, port, q):
     allr = longsignal.allgather_rows(rt, world, dist).numpy()
     m2 = engine.merge_stats([("x", r[0], r[1], r[2]) for r in allr if r[0] > 0])["x"]
     ok = ok and len(allr) == 3 * world and np.allclose(m2, merged[("g", "long")], rtol=1e-15, atol=0)
+    # the SRER target's standard deviation from per-shard sums (longsignal.target_std): every rank gets the bits a single
+    # rank gets from the same shard plan
+    sig = np.random.default_rng(99).standard_normal(16000 * 3 + 77) * 0.1 + 0.01
+    plan1 = longsignal.plan_ranges(len(sig), 16000, 960, 240, 1)
+    planw = longsignal.plan_ranges(len(sig), 16000, 960, 240, world)
+    std_w = longsignal.target_std(sig, planw, rank, world, dist, "cpu")
+    std_1 = longsignal.target_std(sig, plan1, 0, 1, None, "cpu")
+    ok = ok and std_w == std_1 and abs(std_w - np.std(sig)) < 1e-15
     q.put((rank, merged[("g", "long")], (first, last), bool(ok), int(sent)))
     dist.destroy_process_group()
 

@@ -1,5 +1,34 @@
+#!/bin/bash
+# Round-2 evidence on one B200 (run through gpurun from the repo root): bench lines, ncu launch list and full-set captures
+# of the same commands (taken AFTER the plain runs exited 0), parity table, per-configuration timings.  Outputs land in
+# gpurun_out/ (the .ncu-rep files are exported to CSV on the box and removed: gpurun brings back at most 64 MiB); the
+# summaries kept for the judge are copied to profiles/ (see profiles/r02_ncu_summary.md).
+#   tools/evidence_run.sh plain   - bench lines, parity, timings
+#   tools/evidence_run.sh ncu     - profiler passes
 set -x
-python bench.py --steps 2 --warmup 3 > gpurun_out/r02_bench_mid.json 2> gpurun_out/r02_bench_mid.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches_mid.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02_ncu_launches_mid.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name regex:'k_gram_warp|k_chol_solve|k_basis|k_interp_hw|k_synth' --launch-skip 12 --launch-count 12 -o gpurun_out/prof_r02_mid python tools/kernel_times.py 20 1 > gpurun_out/r02_ncu_full_mid.log 2>&1
-ls -la gpurun_out/prof_r02_mid.ncu-rep
+O=gpurun_out
+if [ "$1" != "ncu" ]; then
+python bench.py > $O/r02_bench_final.json 2> $O/r02_bench_final.err || exit 1
+python bench.py --impl reference > $O/r02_bench_final_ref.json 2> $O/r02_bench_final_ref.err
+python tools/parity_report.py > $O/r02_parity.md 2> $O/r02_parity.err
+python tools/dropin_timing.py > $O/r02_dropin_timing.txt 2>&1
+python tools/c4_timing.py 0.25 2 > $O/r02_c4_final.json 2> $O/r02_c4_final.err
+python tools/config_timings.py > $O/r02_config_timings.md 2> $O/r02_config_timings.err
+fi
+if [ "$1" == "plain" ]; then exit 0; fi
+# launch list of the bench command (serialised, cold caches: shares must agree with the live event shares, not the absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/r02_launches_c2.csv \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity-check > $O/r02_ncu_launches.log 2>&1
+# full-set capture of the hot kernels of adaptation 1 of the same workload (two chunks of frames per kernel)
+ncu --set full --clock-control none --import-source on \
+    --kernel-name regex:'k_gram_warp|k_chol_solve|k_basis_fast|k_basis|k_interp_hw|k_synth|k_accept' --launch-skip 14 --launch-count 16 \
+    -o $O/prof_r02_final python tools/kernel_times.py 20 1 > $O/r02_ncu_full.log 2>&1
+ncu -i $O/prof_r02_final.ncu-rep --page raw --csv > $O/r02_ncu_raw_c2.csv 2>/dev/null
+ncu -i $O/prof_r02_final.ncu-rep --page source --csv --kernel-name regex:'k_gram_warp' > $O/r02_ncu_source_gram.csv 2>/dev/null
+rm -f $O/prof_r02_final.ncu-rep
+# config c4 (P = 1,186): panel Cholesky kernels
+ncu --set full --clock-control none --import-source on --kernel-name regex:'k_gram_warp|k_chol_update|k_chol_solve|k_basis_fast' \
+    --launch-skip 12 --launch-count 24 -o $O/prof_r02_c4 python tools/c4_timing.py 0.25 2 > $O/r02_ncu_c4.log 2>&1
+ncu -i $O/prof_r02_c4.ncu-rep --page raw --csv > $O/r02_ncu_raw_c4.csv 2>/dev/null
+rm -f $O/prof_r02_c4.ncu-rep
+du -sh $O
