@@ -250,7 +250,8 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
                 N = max(120, round((pitchPeriods / 2) * (fs / f0)))                 # :191
                 window_lengths[i] = N
                 window = np.blackman(2 * N + 1)                                     # :194
-                amps, slopes = iqhmLS_complexamps(s[c - N:c + N + 1], f0range, window, fs)
+                win_idx = np.arange(c - N, c + N + 1)       # fancy index like :192-196: a negative start wraps
+                amps, slopes = iqhmLS_complexamps(s[win_idx], f0range, window, fs)
                 fmis = np.zeros(2 * K + 1)                                          # :197
             else:
                 N = window_lengths[i]
@@ -264,14 +265,15 @@ def eaqhm_oracle(s, fs, f0s, voiced5, frame_step, f0min, Kmax, *, step=15, maxAd
                     K = 1
                 else:
                     K = act[-1] + 1                                                 # :248
-                fm = fm_current[c - N:c + N + 1][:, act]
-                am = am_current[c - N:c + N + 1][:, act]
+                win_idx = np.arange(c - N, c + N + 1)       # :199,244-245 (fancy index: wraps like the reference)
+                fm = fm_current[win_idx][:, act]
+                am = am_current[win_idx][:, act]
                 for j in range(len(act)):
                     fm[:, j], am[:, j] = fill_track_gaps(fm[:, j], am[:, j])
                 zc = np.zeros((2 * N + 1, 1))
                 fm_all = np.concatenate((-fm[::-1], zc, fm), axis=1)                # :284 flipud reverses TIME (Q2)
                 am_all = np.concatenate((am[::-1], zc, am), axis=1)                 # :285
-                amps_t, slopes_t = eaqhmLS_complexamps(s[c - N:c + N + 1], am_all, fm_all, window, fs)
+                amps_t, slopes_t = eaqhmLS_complexamps(s[win_idx], am_all, fm_all, window, fs)
                 with np.errstate(all="ignore"):
                     fmis_t = fs / (2 * np.pi) * (amps_t.real * slopes_t.imag - amps_t.imag * slopes_t.real) \
                         / np.abs(amps_t) ** 2                                       # :297

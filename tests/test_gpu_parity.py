@@ -626,3 +626,43 @@ def test_batched_elliptic_filter_on_the_gpu_equals_scipy_bitwise():
         ys = preprocess.ellipFilter_batch_gpu(sigs, fs, fc, ftype)
         for s, y in zip(sigs, ys):
             assert (y == preprocess.ellipFilter(s, fs, fc, ftype)).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def test_windows_that_wrap_to_the_end_of_the_signal_match_the_oracle_and_are_refused_by_the_streamed_engine():
+    """A window that starts before sample 0 is read from the END of the signal by the reference's fancy index
+    (functions.py:196,244-245 with negative start): half window N = 533 > analysisWindow*step = 480 at f0 = 45 Hz.  (The
+    reference only survives such a signal when its last frames are unvoiced - a window past the end raises IndexError -
+    hence the voiced-only flags.)  The monolithic engine reproduces the wrap; a frame range cannot."""
+    from eaqhm_b200 import host, longsignal, synthetic
+    cfg = dict(fs=16000, duration=0.2, seed=31, f0_of_t=lambda t: 45.0 + 0 * t)
+    s, f0s = synthetic.make(cfg)
+    n5 = len(np.arange(1, len(s), 80))
+    voiced5 = np.zeros(n5, bool)
+    voiced5[:14] = True
+    Kmax = host.harmonic_capacity(16000, f0s)[1]
+    ft = host.FrameTables(len(s), 16000, f0s, voiced5, 80, Kmax)
+    assert len(ft.wrapping_frames()) >= 3
+    det = host.voiced_only_target(s, voiced5, voiced5, 80)
+    inp = dict(s=s, fs=16000, f0s=f0s, voiced5=voiced5, frame_step=80, f0min=40.0, Kmax=Kmax, det_part=det, step=15,
+               maxAdpt=1, analysisWindow=32)
+    assert_close_results(run_cuda(inp), run_oracle(inp))
+    with pytest.raises(ValueError):
+        longsignal.LongSignalEngine(s, 16000, f0s, voiced5, 80, 40.0, Kmax, shard_seconds=0.1, det_part=det, maxAdpt=1)
+
+
+def test_batch_with_an_utterance_without_voiced_frames():
+    """Ragged batch: one utterance has no analysed frame at all (its reconstruction is the zero DC spline, SRER 0 dB, stop
+    after the second adaptation like functions.py:394-396); its neighbours in the batch are not disturbed."""
+    from eaqhm_b200 import engine, synthetic
+    a = synth_inputs(synthetic.config_c3(5, duration=0.3), maxAdpt=2)
+    b = synth_inputs(synthetic.config_c3(6, duration=0.25), maxAdpt=2)
+    b["voiced5"] = np.zeros_like(b["voiced5"])
+    ra, rb = engine.Engine([utterance(a), utterance(b)], maxAdpt=2).run()
+    alone = run_cuda(a)
+    assert ra.SRER == alone.SRER and (ra.s_recon == alone.s_recon).all()
+    ob = run_oracle(b)
+    assert len(rb.SRER) == len(ob.SRER) == 2 and np.abs(np.array(rb.SRER) - np.array(ob.SRER)).max() <= 1e-12
+    assert not rb.isVoiced.any() and np.abs(rb.s_recon).max() == 0.0 and (rb.am == 0).all()
