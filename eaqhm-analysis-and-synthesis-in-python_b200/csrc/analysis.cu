@@ -881,12 +881,18 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lr = lane >> 2, lc = lane & 3;
     double* ring = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 2 * kG2StageDoubles;
-    const long long nitems = (long long)A.nf * items_per_frame;
-    const long long gw = (long long)blockIdx.x * kG2Warps + warp, nw = (long long)gridDim.x * kG2Warps;
+    const int nitems = A.nf * items_per_frame;
     const size_t plane_stride = (size_t)A.Mxmax * A.Lp;
 
-    for (long long item = gw; item < nitems; item += nw) {
-        const int jl = (int)(item / items_per_frame), t = (int)(item - (long long)jl * items_per_frame);
+    // Work items (frame, lower-triangular tile) come off one global queue in frame order: the (up to 11) tiles that share a
+    // 16-column panel of a frame then run at the same time on neighbouring warps and find it in L2, whatever the spread of
+    // window lengths and empty tile slots does to the warps' progress (a static round-robin lets them drift apart)
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(A.counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int jl = item / items_per_frame, t = item - jl * items_per_frame;
         int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
         while (ti * (ti + 1) / 2 > t) ti--;
         while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
@@ -1891,6 +1897,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         const int nsm = eaqhm_sm_count();
         const int Tt16 = (a.Mxmax + 15) / 16, ipf = Tt16 * (Tt16 + 1) / 2;
         const long long nitems = (long long)a.nf * ipf;
+        CHECK_ARG(nitems < (1LL << 31) - 4096);
+        CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(int32_t), st));
         int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
         if ((long long)blocks * kG2Warps > nitems) blocks = (int)((nitems + kG2Warps - 1) / kG2Warps);
         if (gram_variant == 3) LAUNCH(KC_GRAM, st, k_gram_warp<false><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
