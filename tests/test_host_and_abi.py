@@ -197,3 +197,17 @@ def test_compact_parameter_file_round_trip(tmp_path):
     for name in ("s_recon", "ti", "isSpeech", "isVoiced", "a0", "am", "fm", "ph"):
         assert (getattr(back, name) == getattr(res, name)).all(), name
     assert back.SRER == res.SRER and back.n_adapt_best == 1 and back.fs == 16000 and back.step == step
+
+
+def test_roofline_traffic_comes_from_a_committed_ncu_capture():
+    """bench.py's roofline.traffic is parsed from profiles/ncu_traffic.json, which tools/ncu_traffic.py extracts from a
+    committed raw ncu CSV (no hard-coded constant): the file it names exists, and a workload without capture gives null."""
+    import json
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t = json.load(open(os.path.join(root, "profiles", "ncu_traffic.json")))
+    assert os.path.exists(os.path.join(root, t["source"])) and t["workload"] == "c2"
+    v, src = bench.measured_traffic("gram", "c2", 20.0)
+    assert v == t["kernels"]["gram"]["dram_bytes_per_launch"] and v > 1e9 and t["source"] in src
+    assert bench.measured_traffic("gram", "c3", 96.0)[0] is None
+    assert bench.measured_traffic("gram", "c2", 5.0)[0] is None
