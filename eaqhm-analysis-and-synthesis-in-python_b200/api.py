@@ -93,6 +93,7 @@ def make_engine(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=1
     u = make_utterance(s, fs, f0s, speech5, voiced5, frame_step, gender, step, analysisWindow, fullWaveform, partials)
     limit = STREAM_THRESHOLD_BYTES if stream_threshold_bytes is None else stream_threshold_bytes
     stream = world > 1 or 5 * 8 * u.Kmax * len(u.s) > limit
+    ft = None
     if stream and world == 1:
         # a window that wraps to the end of the signal (functions.py:196 with a negative start index) is only
         # reproduced by the monolithic engine: keep such signals there as long as their tracks fit at all
@@ -103,7 +104,7 @@ def make_engine(s, fs, f0s, speech5, voiced5, frame_step, gender="other", step=1
         from .longsignal import LongSignalEngine
         eng = LongSignalEngine(u.s, u.fs, u.f0s, u.voiced5, u.frame_step, u.f0min, u.Kmax, shard_seconds=shard_seconds,
                                det_part=u.det_part, step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods,
-                               analysisWindow=analysisWindow, rank=rank, world=world, dist=dist, **engine_kw)
+                               analysisWindow=analysisWindow, rank=rank, world=world, dist=dist, full_tables=ft, **engine_kw)
         return PathHandle(eng, single=False)
     eng = Engine([u], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods, analysisWindow=analysisWindow, **engine_kw)
     return PathHandle(eng, single=True)

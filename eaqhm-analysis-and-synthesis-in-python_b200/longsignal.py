@@ -214,6 +214,11 @@ class LongSignalEngine:
                                     l0=g_lo - ft.g0, l1=g_hi - ft.g0,         # owned frames, excerpt-local
                                     n_stat=float(own_hi - own_lo)))
             self.h2d_bytes += e.h2d_bytes
+        if self.world > 1:
+            # one exchange of the (still zero) halo rows now: NCCL sets up its peer connections at the first send/recv
+            # between two ranks, which otherwise lands inside the first adaptation
+            exchange_halo_rows(self.new, (self.F_lo - self.S_lo, self.F_hi - self.S_lo), self.H, self.rank, self.world,
+                               self.dist)
         self.tracks_hold = None          # (shard index, adaptation) whose tracks the pool currently holds
         self._copy_stream = self._copy_done = self._copy_prev = self._views = None
         self.exchanged_bytes = 0
