@@ -112,7 +112,8 @@ def test_seams_match_reference_golden(lib):
     assert rc == 0 and np.abs(out - h["pi_out"]).max() <= 1e-12
 
 
-@pytest.mark.parametrize("K,N,seed", [(1, 120, 0), (7, 120, 1), (31, 133, 2), (60, 150, 3), (86, 267, 4)])
+@pytest.mark.parametrize("K,N,seed", [(1, 120, 0), (7, 120, 1), (31, 133, 2), (60, 150, 3), (86, 267, 4),
+                                      (130, 400, 5)])       # the last one: P = 522 unknowns -> panel Cholesky
 def test_iqhm_seam_recovers_known_stationary_harmonics(lib, K, N, seed):
     """Known-answer test: a stationary harmonic signal is recovered at adaptation 0."""
     rng = np.random.default_rng(seed)
@@ -666,3 +667,24 @@ def test_batch_with_an_utterance_without_voiced_frames():
     ob = run_oracle(b)
     assert len(rb.SRER) == len(ob.SRER) == 2 and np.abs(np.array(rb.SRER) - np.array(ob.SRER)).max() <= 1e-12
     assert not rb.isVoiced.any() and np.abs(rb.s_recon).max() == 0.0 and (rb.am == 0).all()
+
+
+def test_fixed_work_mode_keeps_the_reference_result():
+    """bench.py's fixed-work mode (run_device(fixed_adaptations=n): n adaptations, convergence stop disabled) must leave the
+    result the data-dependent loop returns: same SRER values up to the stop, same best adaptation, same waveform, in both
+    engines."""
+    from eaqhm_b200 import engine, longsignal, synthetic
+    inp = synth_inputs(synthetic.config_c2(duration=1.5), maxAdpt=10)
+    a = engine.Engine([utterance(inp)], maxAdpt=10)
+    ra = a.results(*a.run_device())[0]
+    b = engine.Engine([utterance(inp)], maxAdpt=10)
+    n = len(ra.SRER) + 2
+    rb = b.results(*b.run_device(fixed_adaptations=n))[0]
+    assert len(rb.SRER) == n and rb.SRER[:len(ra.SRER)] == ra.SRER and rb.n_adapt_best == ra.n_adapt_best
+    assert (rb.s_recon == ra.s_recon).all() and (rb.am == ra.am).all() and (rb.ph == ra.ph).all()
+    la = longsignal.LongSignalEngine(inp["s"], 16000, inp["f0s"], inp["voiced5"], 80, inp["f0min"], inp["Kmax"], shard_seconds=0.5)
+    xa = la.results(*la.run_device())
+    lb = longsignal.LongSignalEngine(inp["s"], 16000, inp["f0s"], inp["voiced5"], 80, inp["f0min"], inp["Kmax"], shard_seconds=0.5)
+    xb = lb.results(*lb.run_device(fixed_adaptations=len(xa.SRER) + 2))
+    assert xb.SRER[:len(xa.SRER)] == xa.SRER and xb.n_adapt_best == xa.n_adapt_best and (xb.s_recon == xa.s_recon).all()
+    assert (xb.am == xa.am).all()

@@ -117,6 +117,7 @@ if __name__ == "__main__":
     print("# Round 2 ncu evidence (B200, sm_100a; recipe: tools/evidence_run.sh, generated by tools/ncu_summary.py)\n")
     launch_list(a.launches, a.bench)
     titles = ["`ncu --set full --clock-control none`: hot kernels of adaptation 1 of the default c2 step (two chunks of frames per kernel)",
-              "`ncu --set full`: config c4 (48 kHz, P = 1,186), panel Cholesky"]
+              "`ncu --set full`: config c4 (48 kHz, P = 1,186), panel Cholesky",
+              "`ncu --set full`: config c4, adaptive basis and Gram"]
     for i, p in enumerate(a.raw):
         full_set(p, titles[min(i, len(titles) - 1)])
