@@ -1122,7 +1122,7 @@ __global__ void __launch_bounds__(256) k_gram_toeplitz(AnaArgs A) {
 // dealt round-robin to a persistent grid.
 // ---------------------------------------------------------------------------------------
 constexpr int kPanelW = 48;                           // columns per panel (three 16-wide block columns)
-constexpr int kPanelMinP = 480;                       // systems at least this large take the panel factorisation
+constexpr int kPanelMinP = 512;                       // systems at least this large take the panel factorisation
 constexpr int kUK = 8;                                // factor columns per pipeline stage
 constexpr int kUPitch = 12;                           // row pitch of a stage in double2: 8 + 4 pad = 192 B == 64 mod 128
 constexpr int kUStage = (16 + kPanelW) * kUPitch;     // double2 per stage: 16 A rows, then 48 B rows
@@ -1910,8 +1910,8 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     // experiment knob (tools only): EAQHM_CHOL_WARPS in {1,2,4} warps per frame
     static int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
     CHECK_ARG(xs_bytes - pad <= 32 * 1024);
-    // Two-level (panel) factorisation for large systems: measured cross-over between P = 346 (single kernel 19 % faster)
-    // and P = 586 (panels 20 % faster; P = 1,186: 43 %), profiles/r02_chol_experiments.md.  Experiment knobs (tools only):
+    // Two-level (panel) factorisation for large systems: measured cross-over at P ~ 510 (P = 486: single kernel 2.5 %
+    // faster; P = 538: panels 6 % faster; P = 586: 20 %; P = 1,186: 43 %), profiles/r02_chol_experiments.md.  Experiment knobs (tools only):
     // EAQHM_CHOL_PANEL=0/1 forces one or the other; EAQHM_CHOL_UPD_3M=0 forms the panel update's complex products from
     // four real products
     static const int panel_env = getenv("EAQHM_CHOL_PANEL") ? atoi(getenv("EAQHM_CHOL_PANEL")) : -1;
