@@ -81,6 +81,7 @@ _SIGNATURES = {
     "eaqhm_profile_name": (C.c_char_p, [C.c_int]),
     "eaqhm_profile_read": (C.c_int, [c_f64p, c_i64p, C.c_int32]),
     "eaqhm_analysis_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "eaqhm_analysis_pipeline_sets": (C.c_int, []),
     "eaqhm_analysis": (C.c_int, [C.POINTER(Tables), C.c_void_p, C.POINTER(Tracks), C.POINTER(Knots), C.c_void_p,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),

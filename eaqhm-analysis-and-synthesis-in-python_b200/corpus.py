@@ -3,7 +3,9 @@ to the ranks, analysed in memory-sized batches that adapt in lockstep on one GPU
 utterance takes its own convergence decision (functions.py:394-396), ranks never wait for each other.
 
 Host preprocessing of an utterance (wav read, SWIPE', voicing flags: everything `load(i)` does) runs in a small
-thread pool a few utterances ahead of the GPU, so the device does not idle while the next batch is prepared.
+thread pool a few utterances ahead of the GPU, so the device does not idle while the next batch is prepared; the
+hand-over of a batch's results (wait for the device -> host copy, per-utterance host arrays) runs on a worker thread
+while the next batch is already adapting (two alternating sets of pinned staging buffers).
 """
 from concurrent.futures import ThreadPoolExecutor
 
@@ -41,7 +43,7 @@ def analyze_corpus(n_utterances, load, rank=0, world=1, batch_bytes=16 << 30, lo
     `load(i) -> engine.Utterance` does the host preprocessing of utterance i (api.make_utterance on a wav, or a
     synthetic generator).  Utterances are analysed in the order of their index within the rank's share."""
     mine = partition_round_robin(n_utterances, rank, world)
-    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool, ThreadPoolExecutor(max_workers=1) as handover:
         pending = []                                   # [(index, future)] in order
         nxt = 0
 
@@ -51,6 +53,7 @@ def analyze_corpus(n_utterances, load, rank=0, world=1, batch_bytes=16 << 30, lo
                 pending.append((mine[nxt], pool.submit(load, mine[nxt])))
                 nxt += 1
         top_up()
+        previous, nbatch = None, 0                     # (batch, future of its results) still being handed over
         while pending:
             batch, kmax = [], 0
             while pending:
@@ -58,15 +61,23 @@ def analyze_corpus(n_utterances, load, rank=0, world=1, batch_bytes=16 << 30, lo
                 u = fut.result()
                 new_k = max(kmax, u.Kmax)
                 total = sum(len(b.s) for _, b in batch) + len(u.s)
-                if batch and (TRACK_ARRAYS * new_k + 4) * total * 8 > batch_bytes:
+                # two batches are alive at a time (one adapting, one being handed over): each gets half the budget
+                if batch and (TRACK_ARRAYS * new_k + 4) * total * 8 > batch_bytes // 2:
                     break
                 batch.append((i, u))
                 kmax = new_k
                 pending.pop(0)
                 top_up()
             eng = Engine([u for _, u in batch], step=step, maxAdpt=maxAdpt, pitchPeriods=pitchPeriods,
-                         analysisWindow=analysisWindow, **engine_kw)
-            results = eng.run()
+                         analysisWindow=analysisWindow, staging_set=nbatch % 2, **engine_kw)
+            eng.prepare_readback()
+            out = eng.run_device(prefetch_results=True)
+            fut = handover.submit(eng.results, *out)
             del eng
-            for (i, _), r in zip(batch, results):
+            if previous is not None:
+                for (i, _), r in zip(previous[0], previous[1].result()):
+                    yield i, r
+            previous, nbatch = (batch, fut), nbatch + 1
+        if previous is not None:
+            for (i, _), r in zip(previous[0], previous[1].result()):
                 yield i, r

@@ -1287,16 +1287,16 @@ constexpr bool kChol3M = EAQHM_CHOL_3M != 0;
 #ifndef EAQHM_CHOL_THREADS_PER_SM
 #define EAQHM_CHOL_THREADS_PER_SM 512
 #endif
-template <int kNW>
+template <int kNW, bool kQueue = false>
 __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 32)) k_chol_solve(SolveArgs A, int panel) {
     // panel < 0: the whole factorisation and the back substitution in one launch.  panel = J >= 0: only the block columns
     // of column panel J (kPanelW columns), whose tiles k_chol_update has already updated with every earlier panel, so the
     // update loop below starts at the panel's first column; the back substitution runs in the frame's last panel.
+    // kQueue (panel < 0 only): persistent grid, CTAs take frames off the queue at A.squeue (the chunk pipeline sizes the
+    // grid to the share of an SM it leaves to this kernel; a second launch may join the same queue).
     constexpr int kThreads = kNW * 32;
-    const int jl = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lr = lane >> 2, lc = lane & 3;
-    const int P = 2 * A.Mcols[jl] + 2 * A.dc;
-    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
     const int Pp = A.Pp;
     __shared__ double2 D[kNb][kNb + 1];               // factored diagonal block of the current block column
     __shared__ double2 Tall[kNW][kNb][kNb + 1];       // per-warp staging tile
@@ -1304,7 +1304,18 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
     __shared__ double2 red[kThreads / 16][17];
     __shared__ double Dorig[kNW][kNb];                // diagonal of R before the update: scale of the pivot test
     __shared__ int bad;
+    __shared__ int next_frame;
     extern __shared__ __align__(16) double2 xs[];     // [Pmax] solution
+  for (;;) {
+    int jl = blockIdx.x;
+    if (kQueue) {
+        if (tid == 0) next_frame = atomicAdd(A.squeue, 1);
+        __syncthreads();
+        jl = next_frame;
+        if (jl >= A.nf) return;
+    }
+    const int P = 2 * A.Mcols[jl] + 2 * A.dc;
+    double2* RF = A.R + (size_t)jl * (A.Pmax + 1) * A.Pp;
     if (tid == 0) bad = 0;
     __syncthreads();
 #ifdef EAQHM_CHOL_TIMING
@@ -1541,6 +1552,9 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
 #endif
     double2* xo = A.x + (size_t)jl * A.Pmax;
     for (int p = tid; p < P; p += kThreads) xo[p] = xs[p];
+    if (!kQueue) return;
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1855,6 +1869,17 @@ size_t basis_smem_bytes(int Lp, int nwb) {
 
 }  // namespace
 
+// Chunks of frames are pipelined through `nsets` copies of the per-chunk scratch (see eaqhm_analysis): while the Cholesky of
+// chunk c runs, the basis and Gram kernels of chunk c+1 fill the other copy.  EAQHM_PIPELINE=1 keeps one copy (serial chunks).
+int eaqhm_pipeline_sets() {
+    static const int n = [] {
+        const char* e = getenv("EAQHM_PIPELINE");
+        const int v = e ? atoi(e) : kDefaultSets;
+        return v < 1 ? 1 : (v > kMaxSets ? kMaxSets : v);
+    }();
+    return n;
+}
+
 AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max) {
     AnaLayout l;
     l.nnz_max = nnz_max;
@@ -1862,8 +1887,10 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
     l.Pmax = 2 * l.Mxmax + 2;
     l.Pp = (int32_t)align_up(l.Pmax, kNb);
     l.Lp = (int32_t)align_up(2 * N_max + 1, 4);
+    l.nsets = eaqhm_pipeline_sets();
     int64_t o = 0;
     l.off_fb = o;  o = align_up(o + G, 256);
+    const int64_t set0 = o;                     // offsets below are those of set 0; set s lies s * set_stride further
     l.off_M = o;   o = align_up(o + (int64_t)chunk * 4 * 2, 256);
     l.off_act = o; o = align_up(o + (int64_t)chunk * nnz_max * 2, 256);
     l.off_slow = o; o = align_up(o + (int64_t)chunk * nnz_max, 256);
@@ -1871,11 +1898,12 @@ AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_
     l.off_R = o;   o = align_up(o + (int64_t)chunk * (l.Pmax + 1) * l.Pp * 16, 256);
     l.off_x = o;   o = align_up(o + (int64_t)chunk * l.Pmax * 16, 256);
     l.off_cnt = o; o = align_up(o + 256, 256);
-    l.total = o;
+    l.set_stride = o - set0;
+    l.total = set0 + (int64_t)l.nsets * l.set_stride;
     return l;
 }
 
-int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
+static int solve_attributes() {
     static DeviceOnce solve_once;               // function attributes are per device
     if (const int dev = solve_once.claim(); dev != -1) {
         CHECK_ARG(dev >= 0);
@@ -1883,27 +1911,39 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
         CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
         CUDA_TRY(cudaFuncSetAttribute(k_gram_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGram2Smem));
         CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_chol_solve<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(k_chol_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdSmem));
         CUDA_TRY(cudaFuncSetAttribute(k_chol_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdSmem));
     }
+    return EAQHM_OK;
+}
+
+int eaqhm_launch_gram(const SolveArgs& a, cudaStream_t st, int ctas_per_sm, bool reset_queue) {
+    if (int rc = solve_attributes(); rc != EAQHM_OK) return rc;
     // experiment knob (tools only): EAQHM_GRAM_VARIANT=1 selects the CTA-tiled kernel, 3 the warp kernel with four real
     // products per complex product; default: warp kernel with three (3M)
     static int gram_variant = getenv("EAQHM_GRAM_VARIANT") ? atoi(getenv("EAQHM_GRAM_VARIANT")) : 0;
-    if (do_gram && gram_variant == 1) {
+    if (gram_variant == 1) {
+        if (!reset_queue) return EAQHM_OK;                      // no queue: the first launch covers every tile
         const int Tt = (a.Mxmax + kGT - 1) / kGT;
         dim3 grid(Tt * (Tt + 1) / 2, a.nf);
         LAUNCH(KC_GRAM, st, k_gram<<<grid, 128, kGramSmem, st>>>(a));
-    } else if (do_gram) {
-        const int nsm = eaqhm_sm_count();
-        const int Tt16 = (a.Mxmax + 15) / 16, ipf = Tt16 * (Tt16 + 1) / 2;
-        const long long nitems = (long long)a.nf * ipf;
-        CHECK_ARG(nitems < (1LL << 31) - 4096);
-        CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(int32_t), st));
-        int blocks = 2 * nsm;                                   // persistent: two CTAs per SM
-        if ((long long)blocks * kG2Warps > nitems) blocks = (int)((nitems + kG2Warps - 1) / kG2Warps);
-        if (gram_variant == 3) LAUNCH(KC_GRAM, st, k_gram_warp<false><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
-        else LAUNCH(KC_GRAM, st, k_gram_warp<true><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
+        return EAQHM_OK;
     }
+    const int nsm = eaqhm_sm_count();
+    const int Tt16 = (a.Mxmax + 15) / 16, ipf = Tt16 * (Tt16 + 1) / 2;
+    const long long nitems = (long long)a.nf * ipf;
+    CHECK_ARG(nitems < (1LL << 31) - 4096);
+    if (reset_queue) CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(int32_t), st));
+    int blocks = ctas_per_sm * nsm;                             // persistent grid
+    if ((long long)blocks * kG2Warps > nitems) blocks = (int)((nitems + kG2Warps - 1) / kG2Warps);
+    if (gram_variant == 3) LAUNCH(KC_GRAM, st, k_gram_warp<false><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
+    else LAUNCH(KC_GRAM, st, k_gram_warp<true><<<blocks, kG2Warps * 32, kGram2Smem, st>>>(a, ipf));
+    return EAQHM_OK;
+}
+
+int eaqhm_launch_solve(const SolveArgs& a, cudaStream_t st) {
+    if (int rc = solve_attributes(); rc != EAQHM_OK) return rc;
     // experiment knob (tools only): EAQHM_CHOL_PAD_KB pads the dynamic shared memory to lower the frames per SM
     static const size_t pad = getenv("EAQHM_CHOL_PAD_KB") ? (size_t)atoi(getenv("EAQHM_CHOL_PAD_KB")) * 1024 : 0;
     const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2) + pad;
@@ -1943,10 +1983,68 @@ int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
     return EAQHM_OK;
 }
 
+bool eaqhm_solve_uses_panels(const SolveArgs& a) {
+    static const int panel_env = getenv("EAQHM_CHOL_PANEL") ? atoi(getenv("EAQHM_CHOL_PANEL")) : -1;
+    static const int warps = getenv("EAQHM_CHOL_WARPS") ? atoi(getenv("EAQHM_CHOL_WARPS")) : 2;
+    const bool panels = panel_env >= 0 ? panel_env != 0 : a.Pmax >= kPanelMinP;
+    return panels && warps == 2 && a.Pmax > kPanelW;
+}
+
+int eaqhm_launch_solve_queue(const SolveArgs& a, cudaStream_t st, int ctas_per_sm, bool reset_queue) {
+    if (int rc = solve_attributes(); rc != EAQHM_OK) return rc;
+    CHECK_ARG(a.squeue != nullptr && ctas_per_sm >= 1);
+    const size_t xs_bytes = (size_t)a.Pmax * sizeof(double2);
+    CHECK_ARG(xs_bytes <= 32 * 1024);
+    if (reset_queue) CUDA_TRY(cudaMemsetAsync(a.squeue, 0, sizeof(int32_t), st));
+    const int blocks = min(a.nf, ctas_per_sm * eaqhm_sm_count());
+    LAUNCH(KC_CHOL, st, k_chol_solve<2, true><<<blocks, 64, xs_bytes, st>>>(a, -1));
+    return EAQHM_OK;
+}
+
+int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram) {
+    if (do_gram)
+        if (int rc = eaqhm_launch_gram(a, st, 2, true); rc != EAQHM_OK) return rc;
+    return eaqhm_launch_solve(a, st);
+}
+
+// ---- chunk pipeline: two internal streams and their events, per device ------------------------------------------
+namespace {
+struct Pipe {
+    cudaStream_t sg = nullptr, sc = nullptr;    // build (basis, Gram) and solve (Cholesky, acceptance) streams
+    cudaEvent_t fork = nullptr, sgdone = nullptr, cqueue = nullptr, built[kMaxSets] = {}, solved[kMaxSets] = {};
+};
+int pipe_get(Pipe** out) {
+    static Pipe pipes[kMaxDevices];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CHECK_ARG(dev >= 0 && dev < kMaxDevices);
+    Pipe& P = pipes[dev];
+    if (P.sg == nullptr) {
+        int least = 0, greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        // experiment knob (tools only): EAQHM_PIPE_PRIO 0 = equal priorities, 1 = Gram first (default), 2 = Cholesky first
+        const int prio = getenv("EAQHM_PIPE_PRIO") ? atoi(getenv("EAQHM_PIPE_PRIO")) : 1;
+        CUDA_TRY(cudaStreamCreateWithPriority(&P.sg, cudaStreamNonBlocking, prio == 1 ? greatest : least));
+        CUDA_TRY(cudaStreamCreateWithPriority(&P.sc, cudaStreamNonBlocking, prio == 2 ? greatest : least));
+        CUDA_TRY(cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&P.sgdone, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&P.cqueue, cudaEventDisableTiming));
+        for (int i = 0; i < kMaxSets; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&P.built[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&P.solved[i], cudaEventDisableTiming));
+        }
+    }
+    *out = &P;
+    return EAQHM_OK;
+}
+}  // namespace
+
 extern "C" int64_t eaqhm_analysis_scratch_bytes(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max) {
     if (G < 0 || chunk <= 0 || nnz_max <= 0 || N_max <= 0) return EAQHM_E_ARG;
     return eaqhm_ana_layout(G, chunk, nnz_max, N_max).total;
 }
+
+extern "C" int eaqhm_analysis_pipeline_sets(void) { return eaqhm_pipeline_sets(); }
 
 extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const eaqhm_tracks* cur,
                               const eaqhm_knots* knots, double* best_am, int32_t adapt, int32_t nnz_max,
@@ -1971,17 +2069,22 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     A.adapt = adapt;
     A.nnz_max = l.nnz_max; A.Mxmax = l.Mxmax; A.Pmax = l.Pmax; A.Pp = l.Pp; A.Lp = l.Lp;
     A.fb = base + l.off_fb;
-    A.Mcols = (int32_t*)(base + l.off_M);
-    A.Lrows = A.Mcols + chunk;
-    A.act = (int16_t*)(base + l.off_act);
-    A.slow = base + l.off_slow;
     A.slow_only = 0;
-    A.X = (double*)(base + l.off_X);
-    A.R = (double2*)(base + l.off_R);
-    A.x = (double2*)(base + l.off_x);
     A.status = status;
     A.flop_stats = flop_stats;
     if (tab->nA == 0) return EAQHM_OK;
+    // per-chunk scratch of set `b`
+    auto bind_set = [&](int b) {
+        unsigned char* sb = base + (int64_t)b * l.set_stride;
+        A.Mcols = (int32_t*)(sb + l.off_M);
+        A.Lrows = A.Mcols + chunk;
+        A.act = (int16_t*)(sb + l.off_act);
+        A.slow = sb + l.off_slow;
+        A.X = (double*)(sb + l.off_X);
+        A.R = (double2*)(sb + l.off_R);
+        A.x = (double2*)(sb + l.off_x);
+        return (int32_t*)(sb + l.off_cnt);
+    };
 
     // experiment knob (tools only): EAQHM_BASIS_NWB = warps of a basis CTA that own a column buffer (fewer -> more CTAs per SM)
     static const int nwb_env = getenv("EAQHM_BASIS_NWB") ? atoi(getenv("EAQHM_BASIS_NWB")) : kBasisWarps;
@@ -2009,31 +2112,119 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
         const int nfl = tab->flist ? tab->nF : tab->nA;
         LAUNCH(KC_FALLBACK, st, k_fallback_flags<<<(nfl * 32 + 255) / 256, 256, 0, st>>>(A));
     }
-    for (int j0 = 0; j0 < tab->nA; j0 += chunk) {
-        A.j0 = j0;
-        A.nf = min(chunk, tab->nA - j0);
-        LAUNCH(KC_ACTIVE, st, k_active<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
+
+    // Build half of a chunk (active set, basis planes, rhs / DC rows) on stream `sb`; A is bound to the chunk's set
+    auto build_chunk = [&](cudaStream_t sb) -> int {
+        LAUNCH(KC_ACTIVE, sb, k_active<<<(A.nf * 32 + 255) / 256, 256, 0, sb>>>(A));
         // adaptive basis: fast-path kernel for the columns inside one run (phasor tracks present), k_basis<true> for the rest
         static const bool two_kernels = !(getenv("EAQHM_BASIS_FAST") && atoi(getenv("EAQHM_BASIS_FAST")) == 0);
         const size_t fsm = (size_t)l.Lp * 16;
         const bool fast = adapt > 0 && two_kernels && A.zc_cur != nullptr && A.zs_cur != nullptr && fsm <= 64 * 1024;
         if (adapt == 0) {
-            LAUNCH(KC_BASIS, st, k_basis<false><<<A.nf, kBasisThreads, smem, st>>>(A));
+            LAUNCH(KC_BASIS, sb, k_basis<false><<<A.nf, kBasisThreads, smem, sb>>>(A));
         } else if (fast) {
-            CUDA_TRY(cudaMemsetAsync(A.slow, 0, (size_t)A.nf * l.nnz_max, st));
-            LAUNCH(KC_BASIS, st, k_basis_fast<<<A.nf, kBasisThreads, fsm, st>>>(A));
+            CUDA_TRY(cudaMemsetAsync(A.slow, 0, (size_t)A.nf * l.nnz_max, sb));
+            LAUNCH(KC_BASIS, sb, k_basis_fast<<<A.nf, kBasisThreads, fsm, sb>>>(A));
             A.slow_only = 1;
-            LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
+            LAUNCH(KC_BASIS, sb, k_basis<true><<<A.nf, kBasisThreads, smem, sb>>>(A));
             A.slow_only = 0;
         } else {
-            LAUNCH(KC_BASIS, st, k_basis<true><<<A.nf, kBasisThreads, smem, st>>>(A));
+            LAUNCH(KC_BASIS, sb, k_basis<true><<<A.nf, kBasisThreads, smem, sb>>>(A));
         }
+        return EAQHM_OK;
+    };
+    auto solve_args = [&](int32_t* counter) {
         SolveArgs S;
         S.X = A.X; S.R = A.R; S.x = A.x; S.Mcols = A.Mcols; S.Lrows = A.Lrows;
         S.nf = A.nf; S.Mxmax = l.Mxmax; S.dc = 1; S.Pmax = l.Pmax; S.Pp = l.Pp; S.Lp = l.Lp; S.status = status;
-        S.counter = (int32_t*)(base + l.off_cnt);
-        static const bool use_toeplitz = !(getenv("EAQHM_NO_TOEPLITZ") && atoi(getenv("EAQHM_NO_TOEPLITZ")));
-        const bool toeplitz = adapt == 0 && use_toeplitz;
+        S.counter = counter;
+        S.squeue = nullptr;
+        return S;
+    };
+    static const bool use_toeplitz = !(getenv("EAQHM_NO_TOEPLITZ") && atoi(getenv("EAQHM_NO_TOEPLITZ")));
+    const bool toeplitz = adapt == 0 && use_toeplitz;
+    const int nchunks = (tab->nA + chunk - 1) / chunk;
+
+    if (adapt > 0 && l.nsets >= 2 && nchunks >= 2 && !eaqhm_solve_uses_panels(solve_args(nullptr))) {
+        // Chunk pipeline on two internal streams.  Phase p runs the Cholesky of chunk p beside the basis + Gram of chunk
+        // p+1: the Gram is FP64-pipe bound with few resident warps, the Cholesky load-latency bound with many small CTAs,
+        // so each covers the other's stalls.  Both kernels are persistent grids on work queues, sized to share an SM
+        // (one Gram CTA = 4 warps at 240 registers + four Cholesky CTAs = 8 warps at 128 registers); when one of the
+        // two queues of a phase runs dry, a second launch of the other kernel (queued behind it on the same stream)
+        // joins that kernel's queue and takes over the freed half of every SM.
+        //   sg: build(p+1) . Gram A(p+1) . Cholesky B(p)            sc: Cholesky A(p) . Gram B(p+1) . accept(p)
+        // Same kernels, same per-frame arithmetic: results are bit-identical to the serial order (EAQHM_PIPELINE=1).
+        Pipe* P = nullptr;
+        if (int rc = pipe_get(&P); rc != EAQHM_OK) return rc;
+        static const int g_ctas = getenv("EAQHM_PIPE_GRAM_CTAS") ? atoi(getenv("EAQHM_PIPE_GRAM_CTAS")) : 1;
+        static const int c_ctas = getenv("EAQHM_PIPE_CHOL_CTAS") ? atoi(getenv("EAQHM_PIPE_CHOL_CTAS")) : 4;
+        static const bool helpers = !(getenv("EAQHM_PIPE_HELPERS") && atoi(getenv("EAQHM_PIPE_HELPERS")) == 0);
+        CUDA_TRY(cudaEventRecord(P->fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(P->sg, P->fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(P->sc, P->fork, 0));
+        AnaArgs Ac[kMaxSets];               // arguments of the chunk that lives in each set
+        SolveArgs Sc[kMaxSets];
+        auto bind_chunk = [&](int c) {
+            const int b = c % l.nsets;
+            A.j0 = c * chunk;
+            A.nf = min(chunk, tab->nA - A.j0);
+            int32_t* counter = bind_set(b);
+            Ac[b] = A;
+            Sc[b] = solve_args(counter);
+            Sc[b].squeue = counter + 16;
+            return b;
+        };
+        // phase p = -1 .. nchunks-1: chunk p is factored (p >= 0) while chunk p+1 is built (p+1 < nchunks)
+        for (int p = -1; p < nchunks; p++) {
+            const int bs = p >= 0 ? p % l.nsets : -1;                  // set being solved
+            const bool build = p + 1 < nchunks;
+            int bb = -1;
+            if (build) {
+                // the set's previous chunk (p+1-nsets) must be solved and accepted before the set is rewritten
+                if (p + 1 >= l.nsets) CUDA_TRY(cudaStreamWaitEvent(P->sg, P->solved[(p + 1) % l.nsets], 0));
+                bb = bind_chunk(p + 1);
+                A = Ac[bb];
+                if (int rc = build_chunk(P->sg); rc != EAQHM_OK) return rc;
+                CUDA_TRY(cudaMemsetAsync(Sc[bb].counter, 0, sizeof(int32_t), P->sg));
+                CUDA_TRY(cudaEventRecord(P->built[bb], P->sg));
+            }
+            if (p >= 0) {
+                // sc: everything of the previous phase on sg (Gram A of chunk p) is done; Gram B of chunk p ran on sc itself
+                CUDA_TRY(cudaStreamWaitEvent(P->sc, P->sgdone, 0));
+                // ... and the basis kernels of chunk p+1 have had the device to themselves (beside the Cholesky's resident
+                // CTAs they crawl: 96 KB of shared memory per CTA; measured 8.9 ms against 2.5 ms per chunk)
+                if (build) CUDA_TRY(cudaStreamWaitEvent(P->sc, P->built[bb], 0));
+                CUDA_TRY(cudaMemsetAsync(Sc[bs].squeue, 0, sizeof(int32_t), P->sc));
+                CUDA_TRY(cudaEventRecord(P->cqueue, P->sc));
+                if (int rc = eaqhm_launch_solve_queue(Sc[bs], P->sc, build ? c_ctas : 2 * c_ctas, false); rc != EAQHM_OK) return rc;
+            }
+            if (build) {
+                if (int rc = eaqhm_launch_gram(Sc[bb], P->sg, p >= 0 ? g_ctas : 2 * g_ctas, false); rc != EAQHM_OK) return rc;
+                if (p >= 0 && helpers) {
+                    if (int rc = eaqhm_launch_gram(Sc[bb], P->sc, g_ctas, false); rc != EAQHM_OK) return rc;
+                    CUDA_TRY(cudaStreamWaitEvent(P->sg, P->cqueue, 0));
+                    if (int rc = eaqhm_launch_solve_queue(Sc[bs], P->sg, c_ctas, false); rc != EAQHM_OK) return rc;
+                }
+            }
+            CUDA_TRY(cudaEventRecord(P->sgdone, P->sg));
+            if (p >= 0) {
+                CUDA_TRY(cudaStreamWaitEvent(P->sc, P->sgdone, 0));     // Cholesky B of chunk p (on sg) is done
+                A = Ac[bs];
+                LAUNCH(KC_ACCEPT, P->sc, k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, P->sc>>>(A));
+                CUDA_TRY(cudaEventRecord(P->solved[bs], P->sc));
+            }
+        }
+        // sc is in order and its last phase waited for sg: joining sc joins both
+        CUDA_TRY(cudaStreamWaitEvent(st, P->solved[(nchunks - 1) % l.nsets], 0));
+        return EAQHM_OK;
+    }
+
+    for (int j0 = 0; j0 < tab->nA; j0 += chunk) {
+        A.j0 = j0;
+        A.nf = min(chunk, tab->nA - j0);
+        int32_t* counter = bind_set(0);
+        if (int rc = build_chunk(st); rc != EAQHM_OK) return rc;
+        const SolveArgs S = solve_args(counter);
         if (A.a0_real) {
             // adaptation 0 as two real systems per frame (see k_a0_build_real)
             const size_t tsm = ((size_t)(l.Lp / 2 + 2) + 3 * (size_t)(l.Mxmax + 1)) * 8;

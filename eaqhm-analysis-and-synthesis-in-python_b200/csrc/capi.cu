@@ -1,5 +1,6 @@
 // Library identification and error text of the eaQHM B200 C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,7 +26,7 @@ extern "C" int eaqhm_device_count(void) {
 #include <vector>
 namespace {
 std::mutex g_prof_mu;   // launches of different host threads share the accounting below
-struct Pending { int kc; cudaEvent_t e0, e1; };
+struct Pending { int kc; cudaEvent_t e0, e1; cudaStream_t st; };
 bool g_prof_on = false;
 long long g_counts[KC_COUNT] = {0};
 double g_ms[KC_COUNT] = {0};
@@ -35,13 +36,23 @@ cudaEvent_t take_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+// experiment aid (tools only): EAQHM_TRACE=<file> appends one line per timed launch: class, stream, start and end in ms
+// since the first launch of the drained batch (a timeline of the chunk pipeline's two streams)
 void drain() {
+    static const char* trace_path = getenv("EAQHM_TRACE");
+    FILE* tf = (trace_path && !g_pending.empty()) ? fopen(trace_path, "a") : nullptr;
     for (auto& p : g_pending) {
         float ms = 0.f;
         if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess)
             g_ms[p.kc] += ms;
+        if (tf) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, g_pending.front().e0, p.e0);
+            fprintf(tf, "%d %p %.3f %.3f\n", p.kc, (void*)p.st, t0, t0 + ms);
+        }
         g_pool.push_back(p.e0); g_pool.push_back(p.e1);
     }
+    if (tf) { fprintf(tf, "#\n"); fclose(tf); }
     g_pending.clear();
 }
 }  // namespace
@@ -61,7 +72,7 @@ void eaqhm_prof_end(int kc, cudaStream_t st) {
     if (!g_prof_on || t_cur == nullptr) return;
     cudaEvent_t e1 = take_event();
     cudaEventRecord(e1, st);
-    g_pending.push_back({kc, t_cur, e1});
+    g_pending.push_back({kc, t_cur, e1, st});
     t_cur = nullptr;
 }
 

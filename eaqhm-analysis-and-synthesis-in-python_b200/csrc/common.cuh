@@ -99,8 +99,12 @@ __device__ __forceinline__ double warp_max(double v) {
 // ---- analysis stage internals (analysis.cu) -------------------------------------------
 struct AnaLayout {
     int32_t nnz_max, Mxmax, Pmax, Pp, Lp;  // Mxmax = 2*nnz_max generic columns, Pmax = 2*Mxmax+2, Pp = row pitch of R, Lp = pitch of X rows
-    int64_t off_fb, off_M, off_act, off_slow, off_X, off_R, off_x, off_cnt, total;
+    int32_t nsets;                         // copies of the per-chunk scratch (chunk pipeline depth)
+    int64_t off_fb, off_M, off_act, off_slow, off_X, off_R, off_x, off_cnt, set_stride, total;
 };
+constexpr int kMaxSets = 3;
+constexpr int kDefaultSets = 1;   // chunk pipeline measured and not shipped (profiles/r02_chol_experiments.md): EAQHM_PIPELINE=2 enables it
+int eaqhm_pipeline_sets();
 AnaLayout eaqhm_ana_layout(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max);
 
 // Solves `nf` already-built frames: X [nf][2][Mxmax][Lp] (windowed basis planes), Mcols[nf] generic
@@ -111,9 +115,19 @@ struct SolveArgs {
     const int32_t* Lrows;
     int32_t nf, Mxmax, dc, Pmax, Pp, Lp;
     int32_t* status;
-    int32_t* counter;      // work-queue head of the panel update kernel (zeroed by the launcher)
+    int32_t* counter;      // work-queue head of the Gram / panel update kernel (zeroed by the launcher)
+    int32_t* squeue;       // frame-queue head of the persistent Cholesky launches of the chunk pipeline (else unused)
 };
 int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram);
+// The two halves of the above.  The Gram kernel is a persistent grid that takes (frame, tile) items off the queue at
+// a.counter: `ctas_per_sm` sizes the grid, `reset_queue` zeroes the queue head first; a second launch with
+// reset_queue = false (any stream, ordered after the reset) joins the same queue.
+int eaqhm_launch_gram(const SolveArgs& a, cudaStream_t st, int ctas_per_sm, bool reset_queue);
+int eaqhm_launch_solve(const SolveArgs& a, cudaStream_t st);
+// Persistent form of the single-kernel Cholesky (systems below the panel threshold): `ctas_per_sm` CTAs per SM take
+// frames off the queue at a.squeue; a launch with reset_queue = false joins a queue that is already being served.
+int eaqhm_launch_solve_queue(const SolveArgs& a, cudaStream_t st, int ctas_per_sm, bool reset_queue);
+bool eaqhm_solve_uses_panels(const SolveArgs& a);
 
 // spline helpers shared by interp.cu and synth.cu
 __device__ __forceinline__ double spline_eval(double y0, double y1, double m0, double m1, double h, double t1) {

@@ -179,7 +179,7 @@ class Engine:
 
     def __init__(self, utterances, step=15, maxAdpt=10, pitchPeriods=3, analysisWindow=32,
                  device="cuda", chunk=None, scratch_budget_bytes=None, frame_tables=None,
-                 pool=None, phasor_tracks=True):
+                 pool=None, phasor_tracks=True, staging_set=0):
         if not torch.cuda.is_available():
             raise _lib.EaqhmError("no CUDA device: the eaQHM B200 path has no CPU fallback")
         self.L = _lib.lib()
@@ -281,6 +281,7 @@ class Engine:
         self.status = buf("status", 2, torch.int32)
         self.flops = buf("flops", 3)
         nA = int(self.t_alist.numel())
+        self.pipelined = self.L.eaqhm_analysis_pipeline_sets() >= 2
         if chunk is None:
             if scratch_budget_bytes is None:
                 # big launches amortise the tail of the per-frame kernels (profiles/: 40 GB vs 6 GB = -10 % step time);
@@ -293,6 +294,12 @@ class Engine:
                     scratch_budget_bytes = int(min(40 << 30, free // 3))
             per_frame = self.L.eaqhm_analysis_scratch_bytes(0, 1, self.nnz_max, self.N_max)
             chunk = int(max(1, min(nA, scratch_budget_bytes // max(1, per_frame))))
+            if self.pipelined:
+                # chunk pipeline (Cholesky of one chunk beside the basis + Gram of the next): the first Gram and the last
+                # Cholesky overlap nothing, so aim at PIPE_CHUNKS chunks, but keep every launch a few waves of frames
+                want = int(os.environ.get("EAQHM_PIPE_CHUNKS", "6"))
+                floor = int(os.environ.get("EAQHM_PIPE_MIN_CHUNK", "2400"))
+                chunk = int(max(1, min(chunk, max(floor, -(-nA // max(1, want))))))
         self.chunk = int(chunk)
         nb = self.L.eaqhm_analysis_scratch_bytes(G, self.chunk, self.nnz_max, self.N_max)
         self.scratch = _workspace(nb, d)
@@ -318,6 +325,9 @@ class Engine:
         self._copy_stream = None
         self._copy_done = None
         self._views = None
+        # pinned staging buffers are cached per process and tag; two engines whose read-backs overlap in time (the corpus
+        # runner hands the results of one batch to a worker thread while the next batch computes) use different sets
+        self._stag = "" if not staging_set else "#%d" % int(staging_set)
 
     # ------------------------------------------------------------------------------
     def _stream(self):
@@ -332,6 +342,13 @@ class Engine:
         if self.sort_frames and len(al):
             cost = np.concatenate([self.acost[i] for i in range(self.U) if act[i]])
             al = al[np.argsort(-cost, kind="stable")]
+            n = -(-len(al) // self.chunk)
+            if n >= 2 and self.pipelined:
+                # chunk pipeline: every chunk a stratified sample of the cost-ordered list (chunk b takes ranks b, b+n,
+                # b+2n, ...: expensive frames first inside a chunk, equal work per chunk), so that the Cholesky of one
+                # chunk and the Gram of the next stay matched and the two launches that overlap nothing are 1/n of the work
+                perm = np.arange(n * self.chunk).reshape(self.chunk, n).T.ravel()
+                al = al[perm[perm < len(al)]]
         if len(al):
             self.t_alist[:len(al)].copy_(torch.from_numpy(al))
             self.h2d_bytes += al.nbytes
@@ -397,7 +414,8 @@ class Engine:
         ready.record(main)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(ready)
-            self._views = [_to_host(self.s_best, "s")] + [_to_host(x, "k%d" % i) for i, x in enumerate(self.best)]
+            self._views = [_to_host(self.s_best, "s" + self._stag)] + \
+                [_to_host(x, "k%d%s" % (i, self._stag)) for i, x in enumerate(self.best)]
             self._copy_done = torch.cuda.Event()
             self._copy_done.record(self._copy_stream)
 
@@ -467,9 +485,9 @@ class Engine:
 
     def prepare_readback(self):
         """Page-lock the staging buffers of results() ahead of the loop."""
-        _pinned("s", self.s_best.numel(), torch.float64)
+        _pinned("s" + self._stag, self.s_best.numel(), torch.float64)
         for i, x in enumerate(self.best):
-            _pinned("k%d" % i, x.numel(), torch.float64)
+            _pinned("k%d%s" % (i, self._stag), x.numel(), torch.float64)
 
     def run(self, on_adaptation=None):
         """Adaptation loop + copy of the results to host arrays.  Returns one Result per utterance."""

@@ -116,6 +116,11 @@ typedef struct {
  * allocates (torch / cudaMalloc). */
 int64_t eaqhm_analysis_scratch_bytes(int32_t G, int32_t chunk, int32_t nnz_max, int32_t N_max);
 
+/* Copies of the per-chunk scratch inside that size (1 = chunks run one after the other; 2 = while one chunk is
+ * factored the next one's basis and Gram are built on a second internal stream: a caller that wants the overlap
+ * picks `chunk` so that the analysed frames make several chunks).  Environment EAQHM_PIPELINE overrides. */
+int eaqhm_analysis_pipeline_sets(void);
+
 /* ---------------------------------------------------------------------------
  * Stage A — analysis of all frames in tables->alist for adaptation `adapt`
  * (functions.py:176-329): active set + 140 Hz fallback (Q6), track gather, gap
