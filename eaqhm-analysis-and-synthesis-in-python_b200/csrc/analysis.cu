@@ -1284,6 +1284,12 @@ __device__ unsigned long long g_chol_cycles[8];
 #endif
 constexpr bool kChol3M = EAQHM_CHOL_3M != 0;
 
+#ifndef EAQHM_CHOL_ROWSPLIT
+#define EAQHM_CHOL_ROWSPLIT 0
+#endif
+#ifndef EAQHM_CHOL_PREFETCH
+#define EAQHM_CHOL_PREFETCH 0
+#endif
 #ifndef EAQHM_CHOL_THREADS_PER_SM
 #define EAQHM_CHOL_THREADS_PER_SM 512
 #endif
@@ -1393,6 +1399,19 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
                     };
                     load2(pa, pb, kbeg);
                     for (int k0 = kbeg; k0 < jb; k0 += 16) {
+#if EAQHM_CHOL_PREFETCH > 0
+                        {
+                            // L2 prefetch of the A-operand stream kChPf iterations (16 columns each) ahead: 16 rows x 256 B =
+                            // 32 lines, one per lane; past the end of this tile's k range it runs into the warp's next tile
+                            // of the same block column (same k range, next owned row block)
+                            int kp = k0 + EAQHM_CHOL_PREFETCH * 16, ip = i0;
+                            if (kp >= jb) { kp = kbeg + (kp - jb); ip = i0 + kNW * kNb; }
+                            if (kp < jb && ip <= P) {
+                                const double2* pp = RF + (size_t)min(ip + (lane >> 1), P) * Pp + kp + (lane & 1) * 8;
+                                asm volatile("prefetch.global.L2 [%0];" :: "l"(pp));
+                            }
+                        }
+#endif
                         load2(qa, qb, k0 + 8);
                         kstep(pa[0], pb[0]); kstep(pa[1], pb[1]);
                         if (k0 + 16 < jb) load2(pa, pb, k0 + 16);
@@ -1464,6 +1483,43 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
             }
             TMARK(3);       // wait D
             // ---- 3. rows below the diagonal block: W_i <- W_i L_jj^{-H}, one lane per row ------------
+#if EAQHM_CHOL_ROWSPLIT
+            // two lanes per row: lane r solves the real parts, lane r + 16 the imaginary parts of row r, exchanging each
+            // finished entry by one shuffle; the same fused multiply-adds in the same order as the one-lane form below
+            // (bit-identical), on all 32 lanes instead of 16
+            if (have) {
+                const int row = lane & 15, part = lane >> 4, i = i0 + row;
+                const bool valid = i <= P && !(rb == jbk && row < nbc);
+                double own[kNb], oth[kNb];
+#pragma unroll
+                for (int c = 0; c < kNb; c++) {
+                    const double2 t = T[row][c];
+                    own[c] = part ? t.y : t.x;
+                    oth[c] = part ? t.x : t.y;
+                }
+#pragma unroll
+                for (int c = 0; c < kNb; c++) {
+                    if (c < nbc) {
+                        double v = own[c];
+#pragma unroll
+                        for (int cc = 0; cc < kNb; cc++)
+                            if (cc < c) {
+                                const double2 d = D[c][cc];
+                                v = fma(-own[cc], d.x, v);
+                                v = fma(part ? oth[cc] : -oth[cc], d.y, v);
+                            }
+                        own[c] = v * (1.0 / D[c][c].x);
+                        oth[c] = __shfl_xor_sync(0xffffffffu, own[c], 16);
+                    }
+                }
+                if (valid) {
+                    double2* rowp = RF + (size_t)i * Pp + jb;
+#pragma unroll
+                    for (int c = 0; c < kNb; c++)
+                        if (c < nbc && (c >> 3) == part) rowp[c] = part ? make_double2(oth[c], own[c]) : make_double2(own[c], oth[c]);
+                }
+            }
+#else
             if (have && lane < kNb) {
                 const int i = i0 + lane;
                 // rows of the diagonal tile that lie below the (possibly partial) diagonal block - the rhs row P in
@@ -1487,6 +1543,7 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
                     for (int c = 0; c < kNb; c++) if (c < nbc) rowp[c] = W[c];
                 }
             }
+#endif
             __syncwarp();
             TMARK(4);       // solve rows
         }
