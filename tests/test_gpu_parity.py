@@ -300,6 +300,26 @@ def test_chunked_analysis_equals_unchunked_bitwise():
     assert a.SRER == b.SRER and (a.s_recon == b.s_recon).all() and (a.am == b.am).all()
 
 
+def test_chunk_pipeline_equals_serial_chunks_bitwise():
+    """EAQHM_PIPELINE=2 (experiment knob: the Cholesky of one chunk of frames on a second internal stream beside the
+    basis + Gram of the next chunk, both kernels persistent on work queues, stratified chunk order) against the shipped
+    serial chunk order: the same kernels run the same per-frame arithmetic, so every output is bit-identical.  The
+    library reads the knob once per process, hence two child processes."""
+    import json, os, subprocess, sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py")
+    out = {}
+    for sets in ("1", "2"):
+        env = dict(os.environ, EAQHM_PIPELINE=sets)
+        r = subprocess.run([sys.executable, probe, "260"], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[sets] = json.loads(r.stdout.strip().splitlines()[-1])
+    a, b = out["1"], out["2"]
+    assert a["sets"] == 1 and b["sets"] == 2
+    assert b["frames"] >= 4 * b["chunk"]                 # several phases: first Gram alone, mixed phases, last Cholesky alone
+    for k in ("SRER", "s", "am", "fm", "ph", "a0"):
+        assert a[k] == b[k], k
+
+
 def test_basis_fast_path_equals_running_sum_path():
     """The phasor-track fast path of the adaptive basis (k_basis) against the reference-shaped path (gap scan, running
     sum, sincos per sample), selected by passing no phasor tracks through the C ABI: same support, SRER and waveform far
