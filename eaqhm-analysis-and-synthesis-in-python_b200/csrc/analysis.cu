@@ -1283,6 +1283,7 @@ __device__ unsigned long long g_chol_cycles[8];
 #define EAQHM_CHOL_3M 0
 #endif
 constexpr bool kChol3M = EAQHM_CHOL_3M != 0;
+constexpr int kOneWarpMaxP = 128; // launches whose largest system is at most this size use one warp per frame (eaqhm_launch_solve)
 
 #ifndef EAQHM_CHOL_ROWSPLIT
 #define EAQHM_CHOL_ROWSPLIT 0
@@ -1307,7 +1308,10 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
     __shared__ double2 D[kNb][kNb + 1];               // factored diagonal block of the current block column
     __shared__ double2 Tall[kNW][kNb][kNb + 1];       // per-warp staging tile
     double2 (*T)[kNb + 1] = Tall[warp];
-    __shared__ double2 red[kThreads / 16][17];
+    // row groups of the back substitution's dot products: at least four, so that the one-warp and the two-warp instance
+    // add the same partial sums in the same order (a frame's result must not depend on which instance its launch got)
+    constexpr int kGroups = kThreads / 16 < 4 ? 4 : kThreads / 16;
+    __shared__ double2 red[kGroups][17];
     __shared__ double Dorig[kNW][kNb];                // diagonal of R before the update: scale of the pivot test
     __shared__ int bad;
     __shared__ int next_frame;
@@ -1564,26 +1568,29 @@ __global__ void __launch_bounds__(kNW * 32, EAQHM_CHOL_THREADS_PER_SM / (kNW * 3
             const int r = e >> 4, c2 = e & 15;
             D[r][c2] = (r < nbc && c2 <= r) ? RF[(size_t)(jb + r) * Pp + jb + c2] : make_double2(0.0, 0.0);
         }
-        double2 part = make_double2(0.0, 0.0);
-        if (c < nbc) {
-            constexpr int kStride = kThreads / 16;
-            int i = jb + nbc + rr;
-            for (; i + 3 * kStride < P; i += 4 * kStride) {
-                const double2 l0 = RF[(size_t)i * Pp + jb + c], l1 = RF[(size_t)(i + kStride) * Pp + jb + c];
-                const double2 l2 = RF[(size_t)(i + 2 * kStride) * Pp + jb + c], l3 = RF[(size_t)(i + 3 * kStride) * Pp + jb + c];
-                cfma_conj_a(part, l0, xs[i]); cfma_conj_a(part, l1, xs[i + kStride]);
-                cfma_conj_a(part, l2, xs[i + 2 * kStride]); cfma_conj_a(part, l3, xs[i + 3 * kStride]);
+#pragma unroll
+        for (int grp = rr; grp < kGroups; grp += kThreads / 16) {
+            double2 part = make_double2(0.0, 0.0);
+            if (c < nbc) {
+                constexpr int kStride = kGroups;
+                int i = jb + nbc + grp;
+                for (; i + 3 * kStride < P; i += 4 * kStride) {
+                    const double2 l0 = RF[(size_t)i * Pp + jb + c], l1 = RF[(size_t)(i + kStride) * Pp + jb + c];
+                    const double2 l2 = RF[(size_t)(i + 2 * kStride) * Pp + jb + c], l3 = RF[(size_t)(i + 3 * kStride) * Pp + jb + c];
+                    cfma_conj_a(part, l0, xs[i]); cfma_conj_a(part, l1, xs[i + kStride]);
+                    cfma_conj_a(part, l2, xs[i + 2 * kStride]); cfma_conj_a(part, l3, xs[i + 3 * kStride]);
+                }
+                for (; i < P; i += kStride) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
             }
-            for (; i < P; i += kStride) cfma_conj_a(part, RF[(size_t)i * Pp + jb + c], xs[i]);
+            red[grp][c] = part;
         }
-        red[rr][c] = part;
         const double2 yq = (tid < nbc) ? RF[(size_t)P * Pp + jb + tid] : make_double2(0.0, 0.0);
         __syncthreads();
         if (tid < 32) {
             double2 v = make_double2(0.0, 0.0);
             if (tid < nbc) {
                 v = make_double2(yq.x, -yq.y);
-                for (int r2 = 0; r2 < kThreads / 16; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
+                for (int r2 = 0; r2 < kGroups; r2++) { v.x -= red[r2][tid].x; v.y -= red[r2][tid].y; }
             }
             for (int cc = nbc - 1; cc >= 0; cc--) {
                 double2 xc = make_double2(0.0, 0.0);
@@ -2033,6 +2040,15 @@ int eaqhm_launch_solve(const SolveArgs& a, cudaStream_t st) {
         }
         return EAQHM_OK;
     }
+    // Small systems factor faster with one warp per frame (16 frames per SM, no CTA barrier): measured -21 % at P 62-126
+    // (config c5), equal at P 106-194 (SA19), +12 % at P ~ 200-346 (c2, c3) (profiles/r02_chol_experiments.md).  The
+    // per-frame P is only known on the device, so the choice is per launch, by the launch's largest possible system; a
+    // per-frame split (two launches whose CTAs exit when the frame belongs to the other) was measured and costs the large
+    // workloads 1-2 % in empty CTAs.  EAQHM_CHOL_WARPS forces either.
+    if (!getenv("EAQHM_CHOL_WARPS") && a.Pmax <= kOneWarpMaxP) {
+        LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a, -1));
+        return EAQHM_OK;
+    }
     if (warps == 1) LAUNCH(KC_CHOL, st, k_chol_solve<1><<<a.nf, 32, xs_bytes, st>>>(a, -1));
     else if (warps == 4) LAUNCH(KC_CHOL, st, k_chol_solve<4><<<a.nf, 128, xs_bytes, st>>>(a, -1));
     else if (warps == 8) LAUNCH(KC_CHOL, st, k_chol_solve<8><<<a.nf, 256, xs_bytes, st>>>(a, -1));
@@ -2287,7 +2303,11 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
             const size_t tsm = ((size_t)(l.Lp / 2 + 2) + 3 * (size_t)(l.Mxmax + 1)) * 8;
             CHECK_ARG(tsm <= 48 * 1024);
             LAUNCH(KC_GRAM, st, k_a0_build_real<<<A.nf, 256, tsm, st>>>(A));
-            LAUNCH(KC_CHOL, st, k_chol_real<2><<<2 * A.nf, 64, (size_t)(l.Mxmax + 2) * 8, st>>>(A));
+            // one warp per real system (2K+1 <= 173 unknowns): 1-3 % faster than two on every configuration
+            // (profiles/r02_chol_experiments.md); experiment knob (tools only): EAQHM_CHOL_REAL_WARPS=2
+            static const int real_warps = getenv("EAQHM_CHOL_REAL_WARPS") ? atoi(getenv("EAQHM_CHOL_REAL_WARPS")) : 1;
+            if (real_warps == 1) LAUNCH(KC_CHOL, st, k_chol_real<1><<<2 * A.nf, 32, (size_t)(l.Mxmax + 2) * 8, st>>>(A));
+            else LAUNCH(KC_CHOL, st, k_chol_real<2><<<2 * A.nf, 64, (size_t)(l.Mxmax + 2) * 8, st>>>(A));
             LAUNCH(KC_ACCEPT, st, k_accept<<<(A.nf * 32 + 255) / 256, 256, 0, st>>>(A));
             continue;
         }

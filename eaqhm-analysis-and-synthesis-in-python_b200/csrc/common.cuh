@@ -116,7 +116,7 @@ struct SolveArgs {
     int32_t nf, Mxmax, dc, Pmax, Pp, Lp;
     int32_t* status;
     int32_t* counter;      // work-queue head of the Gram / panel update kernel (zeroed by the launcher)
-    int32_t* squeue;       // frame-queue head of the persistent Cholesky launches of the chunk pipeline (else unused)
+    int32_t* squeue = nullptr;   // frame-queue head of the persistent Cholesky launches of the chunk pipeline (else unused)
 };
 int eaqhm_launch_gram_solve(const SolveArgs& a, cudaStream_t st, bool do_gram);
 // The two halves of the above.  The Gram kernel is a persistent grid that takes (frame, tile) items off the queue at

@@ -320,6 +320,23 @@ def test_chunk_pipeline_equals_serial_chunks_bitwise():
         assert a[k] == b[k], k
 
 
+def test_one_warp_and_two_warp_cholesky_agree_bitwise():
+    """Launches whose largest possible system has P <= 128 factor with one warp per frame (k_chol_solve<1>), the others
+    with two: a frame's result must not depend on which instance its launch got (a shard or a batch of high-pitched
+    frames gets the other instance than the whole signal), so the two instances perform the same operations in the same
+    order - the back substitution's partial sums included.  Forced here through EAQHM_CHOL_WARPS on the same input."""
+    import json, os, subprocess, sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pipeline_probe.py")
+    out = {}
+    for w in ("1", "2"):
+        env = dict(os.environ, EAQHM_CHOL_WARPS=w, EAQHM_PIPELINE="1")
+        r = subprocess.run([sys.executable, probe], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[w] = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("SRER", "s", "am", "fm", "ph", "a0"):
+        assert out["1"][k] == out["2"][k], k
+
+
 def test_basis_fast_path_equals_running_sum_path():
     """The phasor-track fast path of the adaptive basis (k_basis) against the reference-shaped path (gap scan, running
     sum, sincos per sample), selected by passing no phasor tracks through the C ABI: same support, SRER and waveform far
