@@ -480,7 +480,13 @@ __global__ void __launch_bounds__(kBasisThreads) k_basis(AnaArgs A) {
 // window) is flagged in A.slow and rebuilt, together with its sums, by k_basis<true> in slow-only mode.  Same
 // arithmetic, operation for operation, as the fast path of k_basis<true>.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBasisThreads, 3) k_basis_fast(AnaArgs A) {
+#ifndef EAQHM_BASIS_FAST_CTAS
+#define EAQHM_BASIS_FAST_CTAS 3
+#endif
+#ifndef EAQHM_BASIS_FAST_UNROLL
+#define EAQHM_BASIS_FAST_UNROLL 4
+#endif
+__global__ void __launch_bounds__(kBasisThreads, EAQHM_BASIS_FAST_CTAS) k_basis_fast(AnaArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int jl = blockIdx.x;
@@ -546,15 +552,16 @@ __global__ void __launch_bounds__(kBasisThreads, 3) k_basis_fast(AnaArgs A) {
         double s_lo = 0.0;
         ColSums cs_;
         cs_.zero();
-        for (int n0 = lane; n0 < L; n0 += 128) {
-            double fq[4], aq[4], cq[4], sq[4];
+        constexpr int kU = EAQHM_BASIS_FAST_UNROLL;             // samples per lane in flight
+        for (int n0 = lane; n0 < L; n0 += 32 * kU) {
+            double fq[kU], aq[kU], cq[kU], sq[kU];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < kU; q++) {
                 const int n = n0 + 32 * q, ns = n < L ? n : 0;
                 fq[q] = fmk[ns]; aq[q] = amk[ns]; cq[q] = zck[ns]; sq[q] = zsk[ns];
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < kU; q++) {
                 const int n = n0 + 32 * q;
                 if (n >= L) break;
                 if (k == 0) {                                                   // in-place fallback of a frame centred here (Q6)
