@@ -2225,7 +2225,9 @@ extern "C" int eaqhm_analysis(const eaqhm_tables* tab, const double* s, const ea
     const bool toeplitz = adapt == 0 && use_toeplitz;
     const int nchunks = (tab->nA + chunk - 1) / chunk;
 
-    if (adapt > 0 && l.nsets >= 2 && nchunks >= 2 && !eaqhm_solve_uses_panels(solve_args(nullptr))) {
+    // (the pipeline needs the queue-driven Gram and the single-kernel Cholesky: not with the panel path or the experiment variants)
+    if (adapt > 0 && l.nsets >= 2 && nchunks >= 2 && !eaqhm_solve_uses_panels(solve_args(nullptr)) &&
+        !getenv("EAQHM_GRAM_VARIANT") && !getenv("EAQHM_CHOL_WARPS")) {
         // Chunk pipeline on two internal streams.  Phase p runs the Cholesky of chunk p beside the basis + Gram of chunk
         // p+1: the Gram is FP64-pipe bound with few resident warps, the Cholesky load-latency bound with many small CTAs,
         // so each covers the other's stalls.  Both kernels are persistent grids on work queues, sized to share an SM
