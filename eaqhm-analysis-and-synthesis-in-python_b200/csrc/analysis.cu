@@ -3,6 +3,8 @@
 // iqhmLS_complexamps :420-470, eaqhmLS_complexamps :472-535).  sm_100a, FP64.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -876,6 +878,9 @@ __global__ void __launch_bounds__(128, 3) k_gram(SolveArgs A) {
 // persistent grid, so ragged frame sizes, partially filled edge tiles and the idle upper warp of diagonal CTA tiles
 // no longer cost barrier stalls (profiles/r01_ncu_summary.md: barrier was the top stall of k_gram).
 // ---------------------------------------------------------------------------------------
+#ifndef EAQHM_GRAM_NOBREAK
+#define EAQHM_GRAM_NOBREAK 0
+#endif
 constexpr int kG2K = 16;                 // samples per stage
 constexpr int kG2P = 20;                 // shared-memory pitch in doubles (== 4 mod 16: conflict-free fragments)
 constexpr int kG2Warps = 4;
@@ -917,6 +922,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
 #pragma unroll
             for (int sj = 0; sj < 2; sj++)
                 act_[si][sj] = (i0 + si * 8 < Mx) && (j0 + sj * 8 < Mx) && (j0 + sj * 8 <= i0 + si * 8);
+        const bool all_act = act_[0][0] && act_[0][1] && act_[1][0] && act_[1][1];
 
         // plain: acc[..][0] = real part, [1] = imaginary part (4 real products per complex product).
         // 3M:    acc[..][0] = Xr^T Xr', [1] = Xi^T Xi', [2] = (Xr - Xi)^T (Xr' + Xi'): 3 real products;
@@ -974,9 +980,10 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
             const double* ai_s = st + (0 * 2 + 1) * 16 * kG2P + lr * kG2P + lc;
             const double* br_s = st + ((diag ? 0 : 1) * 2 + 0) * 16 * kG2P + lr * kG2P + lc;
             const double* bi_s = st + ((diag ? 0 : 1) * 2 + 1) * 16 * kG2P + lr * kG2P + lc;
-#pragma unroll
-            for (int kk = 0; kk < kG2K; kk += 4) {
-                if (c * kG2K + kk >= L) break;                 // k-steps past the window end of the last stage
+            // one k-step (four samples): fragments from the stage, weights n, n^2 applied to the B side, 9 (3M) or 12 DMMAs
+            // per active 8x8 sub-tile.  kAll: all four sub-tiles active - no predicate, no branch
+            auto kstep = [&](auto all_c, int kk) {
+                constexpr bool kAll = decltype(all_c)::value;
                 const double nc = (double)(c * kG2K + kk + lc - N), nc2 = nc * nc;
                 double ar[2], ai[2], ax[2], br[2][3], bi[2][3], bx[2][3];
 #pragma unroll
@@ -996,7 +1003,7 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
                 for (int si = 0; si < 2; si++)
 #pragma unroll
                     for (int sj = 0; sj < 2; sj++)
-                        if (act_[si][sj]) {
+                        if (kAll || act_[si][sj]) {
 #pragma unroll
                             for (int wt = 0; wt < 3; wt++) {
                                 if (k3M) {
@@ -1011,6 +1018,21 @@ __global__ void __launch_bounds__(kG2Warps * 32, 2) k_gram_warp(SolveArgs A, int
                                 }
                             }
                         }
+            };
+#if EAQHM_GRAM_NOBREAK
+            // interior tiles (all four sub-tiles active), every stage but the last: four k-steps as one straight-line block,
+            // so that a k-step's fragment loads and scalings can be scheduled under the previous one's DMMAs
+            if (all_act && c + 1 < nst) {
+#pragma unroll
+                for (int kk = 0; kk < kG2K; kk += 4) kstep(std::true_type{}, kk);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int kk = 0; kk < kG2K; kk += 4) {
+                    if (c * kG2K + kk >= L) break;             // k-steps past the window end of the last stage
+                    kstep(std::false_type{}, kk);
+                }
             }
             __syncwarp();
         }
