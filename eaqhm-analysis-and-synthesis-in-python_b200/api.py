@@ -14,30 +14,41 @@ from .engine import Engine, Utterance
 from .structs import Deterministic
 
 
-def _array_by_index(idx, values):
-    """misc.py:65-93 (arrayByIndex) as the packing step uses it: an object array, dense up to the
-    last index, holding one-element float arrays at ``idx`` and int 0 elsewhere (quirk Q8)."""
-    if len(idx) == 0:
-        raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # misc.py:61-62 via functions.py:409
-    r = np.zeros(int(idx[-1]) + 1, dtype=object)
-    # one (n,1) array per call; its rows are the one-element arrays (views are ~10x cheaper than np.array([v]))
-    for i, v in zip(idx.tolist(), np.array(values, dtype=float).reshape(-1, 1)):
-        r[i] = v
-    return r
-
-
 def pack_det_components(res):
-    """functions.py:151,325-329,404-411: list of Deterministic records, one per frame."""
-    out = []
+    """functions.py:151,325-329,404-411: list of Deterministic records, one per frame.
+
+    The one-element arrays of all frames (quirk Q8: every accepted harmonic's amplitude, frequency and phase is its own
+    array object) are created in three passes over one (n, 1) array each instead of frame by frame; a frame's object
+    array is a slice of them (or a scatter, when a harmonic below the last accepted one was dropped)."""
     ti, sp, vo = res.ti.tolist(), res.isSpeech.tolist(), res.isVoiced.tolist()
+    vmask = np.asarray(res.isVoiced, bool)
+    rows, cols = np.nonzero(res.am[vmask])
+    counts = np.bincount(rows, minlength=int(vmask.sum()))
+    if (counts == 0).any():
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # misc.py:61-62 via functions.py:409
+    offs = np.concatenate(([0], np.cumsum(counts)))
+    last = cols[offs[1:] - 1].tolist() if len(counts) else []
+    offs = offs.tolist()
+
+    def entries(x):
+        v = np.ascontiguousarray(x[vmask][rows, cols], dtype=float).reshape(-1, 1)
+        return np.fromiter(v, dtype=object, count=len(v))       # the rows of v as one-element float arrays
+    va, vf, vp = entries(res.am), entries(res.fm), entries(res.ph)
+    out, j = [], 0
     for i in range(len(ti)):
         d = Deterministic(ti=ti[i], isSpeech=sp[i], isVoiced=vo[i])
         if vo[i]:
-            nz = np.flatnonzero(res.am[i])
+            o0, o1, size = offs[j], offs[j + 1], last[j] + 1
             d.a0 = res.a0[i]
-            d.amplitudes = _array_by_index(nz, res.am[i, nz])
-            d.frange = _array_by_index(nz, res.fm[i, nz])
-            d.pk = _array_by_index(nz, res.ph[i, nz])
+            if size == o1 - o0:                                   # dense up to the last accepted harmonic
+                d.amplitudes, d.frange, d.pk = va[o0:o1].copy(), vf[o0:o1].copy(), vp[o0:o1].copy()
+            else:                                                 # int 0 at the dropped harmonics (misc.py:89-93)
+                c = cols[o0:o1]
+                for name, v in (("amplitudes", va), ("frange", vf), ("pk", vp)):
+                    r = np.zeros(size, dtype=object)
+                    r[c] = v[o0:o1]
+                    setattr(d, name, r)
+            j += 1
         out.append(d)
     return out
 

@@ -89,6 +89,38 @@ def test_pack_det_components_shapes_follow_reference_quirk_q8():
         api.pack_det_components(res)
 
 
+def test_pack_det_components_on_dense_and_gappy_frames():
+    """Batched packing against the per-frame definition (misc.py:65-93 through functions.py:409-411): an object array dense
+    up to the last accepted harmonic, one-element float arrays at the accepted harmonics, int 0 at the dropped ones."""
+    from eaqhm_b200.engine import Result
+    rng = np.random.default_rng(5)
+    G, K = 60, 12
+    am = rng.random((G, K)) + 0.1
+    for i in range(G):
+        am[i, rng.integers(3, K + 1):] = 0.0            # frames end at different harmonics
+    am[rng.random((G, K)) < 0.1] = 0.0                  # dropped harmonics in between
+    am[:, 0] = np.where(am.sum(1) == 0, 0.3, am[:, 0])  # no voiced frame without a harmonic
+    voiced = rng.random(G) > 0.2
+    res = Result(s_recon=np.zeros(4), SRER=[1.0], ti=np.arange(G) * 15, isSpeech=np.ones(G, bool), isVoiced=voiced,
+                 a0=rng.random(G), am=am, fm=am * 1000, ph=am - 0.5)
+    det = api.pack_det_components(res)
+    assert len(det) == G
+    for i, d in enumerate(det):
+        assert d.ti == 15 * i and d.isVoiced is bool(voiced[i]) and d.ak == []
+        if not voiced[i]:
+            assert d.a0 == [] and d.frange == [] and d.pk == [] and not hasattr(d, "amplitudes")
+            continue
+        nz = np.flatnonzero(am[i])
+        assert d.a0 == res.a0[i]
+        for arr, src in ((d.amplitudes, res.am), (d.frange, res.fm), (d.pk, res.ph)):
+            assert arr.dtype == object and arr.shape == (nz[-1] + 1,)
+            for k in range(nz[-1] + 1):
+                if am[i, k] != 0:
+                    assert isinstance(arr[k], np.ndarray) and arr[k].shape == (1,) and arr[k][0] == src[i, k]
+                else:
+                    assert isinstance(arr[k], int) and arr[k] == 0
+
+
 def test_c_abi_exports_every_declared_symbol():
     _lib.build()
     L = ctypes.CDLL(_lib.LIB_PATH)
