@@ -284,14 +284,17 @@ class Engine:
         self.pipelined = self.L.eaqhm_analysis_pipeline_sets() >= 2
         if chunk is None:
             if scratch_budget_bytes is None:
-                # big launches amortise the tail of the per-frame kernels (profiles/: 40 GB vs 6 GB = -10 % step time);
-                # stay within a third of what is free so that two engines can coexist
+                # big launches amortise the tail of the per-frame kernels (profiles/: 40 GB vs 6 GB = -10 % step time, 80 GB
+                # - the 21,270 frames of a 20 s c2 range in one chunk - another -1 %); at most half of what is free: the
+                # workspace is shared by the engines of a process (one process per GPU)
                 ws = _WORKSPACE.get(str(self.device))
                 if ws is not None and ws.numel() >= (8 << 30):
                     scratch_budget_bytes = int(ws.numel())      # reuse the process's workspace (no driver query: ~10 ms)
                 else:
                     free, _ = torch.cuda.mem_get_info(self.device)
-                    scratch_budget_bytes = int(min(40 << 30, free // 3))
+                    # experiment knob (tools only): EAQHM_SCRATCH_GB = budget in GiB, capped at half of what is free
+                    env_gb = os.environ.get("EAQHM_SCRATCH_GB")
+                    scratch_budget_bytes = int(min(int(float(env_gb) * (1 << 30)) if env_gb else 80 << 30, free // 2))
             per_frame = self.L.eaqhm_analysis_scratch_bytes(0, 1, self.nnz_max, self.N_max)
             chunk = int(max(1, min(nA, scratch_budget_bytes // max(1, per_frame))))
             if self.pipelined:
