@@ -148,10 +148,12 @@ def emit(fd, obj):
     os.write(fd, (json.dumps(obj) + "\n").encode())
 
 
-def measured_traffic(kernel, workload, shard_seconds):
+def measured_traffic(kernel, workload, shard_seconds, chunks_now=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
     of this command (profiles/ncu_traffic.json, extracted from the raw ncu CSV by tools/ncu_traffic.py); None when no
-    capture of this workload is committed."""
+    capture of this workload is committed.  The analysed frames of an adaptation are processed in chunks sized by the
+    scratch budget; when this run's chunk count (`chunks_now`) differs from the captured run's, the per-launch figure
+    is rescaled by their ratio (the bytes per adaptation do not depend on the chunking)."""
     try:
         t = json.load(open(NCU_TRAFFIC))
     except Exception:
@@ -159,8 +161,13 @@ def measured_traffic(kernel, workload, shard_seconds):
     e = t.get("kernels", {}).get(kernel)
     if e is None or t.get("workload") != workload or float(t.get("shard_seconds", -1)) != float(shard_seconds):
         return None, "profiles/ncu_traffic.json holds no capture of this kernel / workload"
-    return float(e["dram_bytes_per_launch"]), "%s (%s, %d launches averaged)" % (t.get("source"), e.get("sass_name", kernel),
-                                                                                 int(e.get("launches", 0)))
+    per_launch, note = float(e["dram_bytes_per_launch"]), ""
+    cap = int(t.get("chunks_per_adaptation", 0))
+    if chunks_now and cap and int(chunks_now) != cap:
+        per_launch *= cap / float(chunks_now)
+        note = "; captured with %d launches per adaptation, this run has %d: per-launch figure rescaled" % (cap, int(chunks_now))
+    return per_launch, "%s (%s, %d launches averaged%s)" % (t.get("source"), e.get("sass_name", kernel),
+                                                           int(e.get("launches", 0)), note)
 
 
 def main():
@@ -426,7 +433,10 @@ def main():
     conventional = {"gram": useful["gram"], "chol_solve": useful["chol"], "basis": useful["basis"]}
     achieved = executed[dom] / (kt[dom] * 1e-3) / 1e12 if kt[dom] > 0 else 0.0
     conv = conventional[dom] / (kt[dom] * 1e-3) / 1e12 if kt[dom] > 0 else 0.0
-    traffic, traffic_src = measured_traffic(dom, args.workload, args.shard_seconds)
+    # launches of the dominant kernel per adaptation in this run (its class also counts one launch per chunk at adaptation 0)
+    adapt_run = max(1, len(srer_list))
+    chunks_now = max(1, int(round(prof[dom][1] / args.steps / adapt_run))) if dom in prof else None
+    traffic, traffic_src = measured_traffic(dom, args.workload, args.shard_seconds, chunks_now)
     roofline = {"bound": "tensor", "pipe": "FP64 (DFMA and DMMA share one pipe on sm_100a)", "kernel": dom,
                 "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
                 "achieved_conventional": conv, "frac_conventional": conv / FP64_PEAK_TFLOPS,

@@ -241,5 +241,9 @@ def test_roofline_traffic_comes_from_a_committed_ncu_capture():
     assert os.path.exists(os.path.join(root, t["source"])) and t["workload"] == "c2"
     v, src = bench.measured_traffic("gram", "c2", 20.0)
     assert v == t["kernels"]["gram"]["dram_bytes_per_launch"] and v > 1e9 and t["source"] in src
+    # the capture's two launches per adaptation against a run that processes the adaptation's frames in one chunk
+    v1, src1 = bench.measured_traffic("gram", "c2", 20.0, chunks_now=1)
+    assert v1 == v * t["chunks_per_adaptation"] and "rescaled" in src1
+    assert bench.measured_traffic("gram", "c2", 20.0, chunks_now=t["chunks_per_adaptation"])[0] == v
     assert bench.measured_traffic("gram", "c3", 96.0)[0] is None
     assert bench.measured_traffic("gram", "c2", 5.0)[0] is None

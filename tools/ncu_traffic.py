@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--shard-seconds", type=float, default=20.0)
     ap.add_argument("--command", default="")
+    ap.add_argument("--chunks-per-adaptation", type=int, default=1,
+                    help="launches per kernel and adaptation in the captured run (the analysed frames are processed in chunks "
+                         "sized by the scratch budget): bench.py rescales the per-launch figure to its own chunking")
     args = ap.parse_args()
     rows = list(csv.reader(open(args.csv)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -44,7 +47,8 @@ def main():
                     "dram_bytes_per_launch": sum(by) / len(by), "dram_bytes_total": sum(by),
                     "ms_per_launch_under_ncu": sum(ms) / len(ms)}
     json.dump({"source": args.csv, "command": args.command, "workload": args.workload,
-               "shard_seconds": args.shard_seconds, "kernels": out}, sys.stdout, indent=1)
+               "shard_seconds": args.shard_seconds, "chunks_per_adaptation": args.chunks_per_adaptation, "kernels": out},
+              sys.stdout, indent=1)
     print()
 
 
