@@ -4,5 +4,5 @@ run() { name=$1; shift; rm -f gpurun_out/trace_$name.txt; env EAQHM_TRACE=gpurun
 : > gpurun_out/pipe_trace.jsonl
 run serial EAQHM_PIPELINE=1
 run pipe EAQHM_PIPELINE=2
-run nohelper EAQHM_PIPELINE=2 EAQHM_PIPE_HELPER_CTAS=0
+run nohelper EAQHM_PIPELINE=2 EAQHM_PIPE_HELPERS=0
 run prio0 EAQHM_PIPELINE=2 EAQHM_PIPE_PRIO=0
