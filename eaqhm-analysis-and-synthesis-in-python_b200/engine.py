@@ -15,6 +15,7 @@ import torch
 
 from . import _lib
 from .host import FrameTables
+from .sharding import stratified_chunk_order
 
 
 @dataclass
@@ -350,8 +351,7 @@ class Engine:
                 # chunk pipeline: every chunk a stratified sample of the cost-ordered list (chunk b takes ranks b, b+n,
                 # b+2n, ...: expensive frames first inside a chunk, equal work per chunk), so that the Cholesky of one
                 # chunk and the Gram of the next stay matched and the two launches that overlap nothing are 1/n of the work
-                perm = np.arange(n * self.chunk).reshape(self.chunk, n).T.ravel()
-                al = al[perm[perm < len(al)]]
+                al = al[stratified_chunk_order(len(al), self.chunk)]
         if len(al):
             self.t_alist[:len(al)].copy_(torch.from_numpy(al))
             self.h2d_bytes += al.nbytes

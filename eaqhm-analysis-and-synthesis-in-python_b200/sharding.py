@@ -21,3 +21,16 @@ def contiguous_blocks(n_items, world):
         out.append((start, start + cnt))
         start += cnt
     return out
+
+
+def stratified_chunk_order(n_items, chunk):
+    """Positions of a cost-ordered list re-dealt so that consecutive chunks of `chunk` items are stratified samples of
+    it: chunk b takes ranks b, b + n, b + 2n, ... (n = number of chunks), in rank order inside the chunk.  Used by the
+    chunk pipeline of the analysis stage (EAQHM_PIPELINE=2): equal work per chunk, expensive frames first in each."""
+    import numpy as np
+    n = -(-n_items // chunk)
+    if n < 2:
+        return np.arange(n_items)
+    perm = np.arange(n * chunk).reshape(chunk, n).T.ravel()
+    return perm[perm < n_items]
+

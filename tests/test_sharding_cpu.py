@@ -19,6 +19,25 @@ def test_partitions_cover_everything_once():
         assert max(b - a for a, b in cb) - min(b - a for a, b in cb) <= 1
 
 
+def test_stratified_chunk_order_is_a_balanced_permutation():
+    """Chunk pipeline (EAQHM_PIPELINE=2): the cost-ordered frame list re-dealt into chunks that are stratified samples."""
+    from eaqhm_b200.sharding import stratified_chunk_order
+    rng = np.random.default_rng(3)
+    for n_items, chunk in ((21270, 3545), (1000, 260), (17, 5), (10, 10), (7, 100)):
+        perm = stratified_chunk_order(n_items, chunk)
+        assert sorted(perm.tolist()) == list(range(n_items))
+        cost = np.sort(rng.random(n_items) ** 3)[::-1]            # descending, like the engine's cost order
+        c = cost[perm]
+        nch = -(-n_items // chunk)
+        sums = [c[b * chunk:(b + 1) * chunk].sum() for b in range(nch)]
+        if nch >= 2 and n_items % chunk == 0:
+            assert max(sums) / min(sums) < 1.05                    # equal work per chunk
+            for b in range(nch):                                   # expensive frames first inside every chunk
+                assert (np.diff(c[b * chunk:(b + 1) * chunk]) <= 0).all()
+        if nch == 1:
+            assert (perm == np.arange(n_items)).all()
+
+
 def test_corpus_batches_respect_the_memory_budget():
     sizes, kmaxes = [48000, 48000, 16000, 96000, 48000, 1000], [60, 97, 40, 97, 50, 97]
     per = lambda n, k: (corpus.TRACK_ARRAYS * k + 4) * n * 8
